@@ -1,0 +1,67 @@
+// common.cuh — shared host-side plumbing of libalore_b200 (context, error handling).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/alore_b200.h"
+
+struct alore_ctx {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // ---- ESDF state (device-resident grid map) ----
+  alore_map_geom_t geom{};
+  bool have_map = false;
+  uint8_t* d_occ = nullptr;      // glx*gly
+  double* d_dist = nullptr;      // glx*gly  (SDFmap::distance_buffer_all_ mirror)
+  size_t map_cells = 0;
+  int16_t* d_row = nullptr;      // window-local signed row distances, pitch row_pitch
+  uint32_t* d_blk = nullptr;     // per (32-row block, column): lo16 = min g+ , hi16 = min g-
+  size_t row_cap = 0, blk_cap = 0;
+  int row_pitch = 0;
+  int win[4] = {0, 0, -1, -1};   // min_x, min_y, max_x, max_y of the last update
+  int last_ref_compat = 1;
+  float esdf_kernel_ms = 0.f;
+  const void* dist_host_synced = nullptr;   // host buffer the device copy mirrors
+  // host buffers registered with cudaHostRegister (pinned for async copies)
+  struct Reg { const void* p; size_t bytes; };
+  std::vector<Reg> regs;
+
+  // ---- optimizer scratch (see traj_opt.cu) ----
+  void* opt_scratch = nullptr;
+  size_t opt_scratch_bytes = 0;
+};
+
+inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define ALORE_CUDA(ctx, call)                                                                          \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return alore_fail((ctx), ALORE_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+// Pins a caller-owned host buffer once (best effort) so cudaMemcpyAsync runs at PCIe speed.
+void alore_pin_host(alore_ctx* ctx, const void* p, size_t bytes);
+
+// esdf.cu
+int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,
+                   int ref_compat, cudaStream_t st, int32_t* d_pos_sq, int32_t* d_neg_sq);

@@ -1,0 +1,340 @@
+// esdf.cu — occupancy grid -> signed ESDF, integer-exact separable squared EDT (sm_100a).
+//
+// Replaces the body of SDFmap::updateESDF2d / fillESDF
+// (reference: planning_ddr_opt/utils/plan_env/src/sdf_map.cpp:618-715).
+//
+// Data flow (window of NX x NY cells, y contiguous):
+//   K1  esdf_row_pass   uint8 occupancy -> int16 SIGNED row distance R(x,y):
+//                         free/unknown cell : +d to the nearest Occupied cell in its row (+32767: none)
+//                         Occupied cell     : -d to the nearest non-Occupied cell in its row (-32767: none)
+//                       One value encodes both of the reference's first passes because a cell is a seed of
+//                       exactly one of the two transforms (sdf_map.cpp:635 vs :655-657).
+//   K1b esdf_block_min  per (32-row block, column) minima of g+ and g- (pruning bounds for K2's far search)
+//   K2  esdf_col_pass   exact column transform  val(X) = min_x' (X-x')^2 + g(x')^2  by an expanding search
+//                       with the t*t >= best cut-off, rows staged in shared memory (tile + halo), then
+//                       dist = gi*sqrt(val) and the reference's pos/neg combine (sdf_map.cpp:671-679).
+//   K2q esdf_quirk_col  ref_compat: window-local column 0 is recomputed from the aliased input the
+//                       reference actually reads.
+// All arithmetic on squared distances is int32 (exact); the only FP ops are sqrt.rn.f64, mul.rn.f64 and
+// add.rn.f64, IEEE-identical to the CPU.  HBM-bound by design: 1 B/cell in, 2+2 B/cell intermediate
+// (L2-resident at 4096^2), 8 B/cell out.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int SENT = 32767;
+constexpr int SQ_SENT = SENT * SENT;  // 1073676289: anything >= this is "no seed" (DBL_MAX in the reference)
+constexpr int BLK = 32;               // rows per pruning block
+constexpr int TX = 64, TY = 128, HALO = 32;
+constexpr int ROW_THREADS = 256;
+
+__device__ __forceinline__ int excl_scan_max(int v, int* s_warp, int ident) {
+  // exclusive max-scan over the CTA in thread order; s_warp has blockDim/32 slots
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, t);
+  }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  int carry = ident;
+  for (int i = 0; i < w; i++) carry = max(carry, s_warp[i]);
+  int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = ident;
+  __syncthreads();
+  (void)nw;
+  return max(carry, ex);
+}
+__device__ __forceinline__ int excl_scan_min_rev(int v, int* s_warp, int ident) {
+  // exclusive min-scan from the right (thread t gets min over threads > t)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_down_sync(0xffffffffu, inc, o);
+    if (lane + o < 32) inc = min(inc, t);
+  }
+  if (lane == 0) s_warp[w] = inc;
+  __syncthreads();
+  int carry = ident;
+  for (int i = w + 1; i < nw; i++) carry = min(carry, s_warp[i]);
+  int ex = __shfl_down_sync(0xffffffffu, inc, 1);
+  if (lane == 31) ex = ident;
+  __syncthreads();
+  return min(carry, ex);
+}
+
+// K1: one CTA per window row.  Dynamic smem: [NY+32 bytes occupancy][NY int16 forward distances].
+__global__ void __launch_bounds__(ROW_THREADS)
+esdf_row_pass(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int min_x, int min_y, int NX, int NY,
+              int16_t* __restrict__ R, int pitch) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_warp[ROW_THREADS / 32];
+  const int X = blockIdx.x;
+  const size_t row0 = (size_t)(X + min_x) * gly + min_y;
+  const uint8_t* src = occ + row0;
+  const int shift = (int)((uintptr_t)src & 15);
+  const int nvec = (shift + NY + 15) >> 4;
+  uint8_t* s_raw = smem;
+  const int occ_bytes = ((NY + 31 + 15) >> 4) << 4;
+  int16_t* s_d = reinterpret_cast<int16_t*>(smem + occ_bytes);
+  {
+    const bool aligned_ok = (((uintptr_t)occ & 15) == 0);  // then src - shift never precedes occ
+    const long long off0 = (long long)row0 - shift;        // byte offset in occ of vector 0
+    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+      const long long off = off0 + (long long)v * 16;
+      if (aligned_ok && off + 16 <= (long long)occ_total) {
+        reinterpret_cast<uint4*>(s_raw)[v] = *reinterpret_cast<const uint4*>(occ + off);
+      } else {
+        for (int b = 0; b < 16; b++) {
+          const long long o = off + b;
+          s_raw[v * 16 + b] = (o >= 0 && o < (long long)occ_total) ? occ[o] : 0;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint8_t* s_occ = s_raw + shift;
+
+  const int CH = (NY + ROW_THREADS - 1) / ROW_THREADS;
+  const int c0 = min(threadIdx.x * CH, NY), c1 = min(c0 + CH, NY);
+  const int BIG = 1 << 29;
+  int lastOcc = -1, lastFree = -1, firstOcc = BIG, firstFree = BIG;
+  for (int y = c0; y < c1; y++) {
+    if (s_occ[y] == ALORE_OCCUPIED) { lastOcc = y; if (firstOcc == BIG) firstOcc = y; }
+    else { lastFree = y; if (firstFree == BIG) firstFree = y; }
+  }
+  int lo = excl_scan_max(lastOcc, s_warp, -1);
+  int lf = excl_scan_max(lastFree, s_warp, -1);
+  int no = excl_scan_min_rev(firstOcc, s_warp, BIG);
+  int nf = excl_scan_min_rev(firstFree, s_warp, BIG);
+  for (int y = c0; y < c1; y++) {
+    int d;
+    if (s_occ[y] == ALORE_OCCUPIED) { lo = y; d = (lf < 0) ? SENT : y - lf; }
+    else { lf = y; d = (lo < 0) ? SENT : y - lo; }
+    s_d[y] = (int16_t)d;
+  }
+  for (int y = c1 - 1; y >= c0; y--) {
+    int d2;
+    if (s_occ[y] == ALORE_OCCUPIED) {
+      no = y;
+      d2 = (nf == BIG) ? SENT : nf - y;
+      s_d[y] = (int16_t)(-min((int)s_d[y], d2));
+    } else {
+      nf = y;
+      d2 = (no == BIG) ? SENT : no - y;
+      s_d[y] = (int16_t)min((int)s_d[y], d2);
+    }
+  }
+  __syncthreads();
+  // coalesced store (row start of R is 16-byte aligned: pitch % 8 == 0)
+  int16_t* dst = R + (size_t)X * pitch;
+  const int nv = NY >> 3;
+  for (int v = threadIdx.x; v < nv; v += ROW_THREADS)
+    reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(s_d)[v];
+  for (int y = (nv << 3) + threadIdx.x; y < NY; y += ROW_THREADS) dst[y] = s_d[y];
+}
+
+// K1b: block minima for far-search pruning.  grid (ceil(NY/256), ceil(NX/BLK)).
+__global__ void esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= NY) return;
+  const int x0 = blockIdx.y * BLK, x1 = min(x0 + BLK, NX);
+  int mp = SENT, mn = SENT;
+  for (int x = x0; x < x1; x++) {
+    const int r = R[(size_t)x * pitch + y];
+    mp = min(mp, r > 0 ? r : 0);
+    mn = min(mn, r < 0 ? -r : 0);
+  }
+  blk[(size_t)blockIdx.y * blk_pitch + y] = (uint32_t)mp | ((uint32_t)mn << 16);
+}
+
+// Search rows outside the shared-memory halo, block by block, pruned by the block minima.
+__device__ __noinline__ int esdf_far_search(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk,
+                                            int blk_pitch, int NX, int X, int y, bool neg, int best, int t_start) {
+#pragma unroll 1
+  for (int dir = -1; dir <= 1; dir += 2) {
+    int x = X + dir * t_start;
+    while (x >= 0 && x < NX) {
+      const int d = abs(x - X);
+      if (d * d >= best) break;
+      const int b = x / BLK;
+      const int bend = dir < 0 ? b * BLK : min(b * BLK + BLK - 1, NX - 1);
+      const uint32_t m = blk[(size_t)b * blk_pitch + y];
+      const int mg = neg ? (int)(m >> 16) : (int)(m & 0xffffu);
+      if (d * d + mg * mg < best) {
+        for (int xx = x;; xx += dir) {
+          const int r = R[(size_t)xx * pitch + y];
+          const int dd = xx - X;
+          const int c = ((r < 0) == neg) ? r * r : 0;
+          best = min(best, dd * dd + c);
+          if (xx == bend) break;
+        }
+      }
+      x = bend + dir;
+    }
+  }
+  return best;
+}
+
+__device__ __forceinline__ double esdf_value(int best, bool neg, double gi) {
+  const double root = (best >= SQ_SENT) ? sqrt(DBL_MAX) : sqrt((double)best);
+  const double dv = __dmul_rn(gi, root);               // grid_interval_ * std::sqrt(val)
+  return neg ? __dadd_rn(0.0, __dadd_rn(-dv, gi))      // all = pos(=0); all += (-neg + gi)
+             : dv;
+}
+
+// K2: column pass.  grid (ceil(NY/TY), ceil(NX/TX)), 256 threads = 128 columns x 2 row halves.
+template <bool SQ>
+__global__ void __launch_bounds__(256)
+esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
+              double* __restrict__ dist, int gly, int min_x, int min_y, double gi, int ref_compat,
+              int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  __shared__ __align__(16) int16_t S[TX + 2 * HALO][TY];
+  const int X0 = blockIdx.y * TX, Y0 = blockIdx.x * TY;
+  const int rlo = X0 - HALO;
+  for (int idx = threadIdx.x; idx < (TX + 2 * HALO) * (TY / 8); idx += 256) {
+    const int row = idx / (TY / 8), v = idx % (TY / 8);
+    const int xr = rlo + row, y = Y0 + v * 8;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (xr >= 0 && xr < NX && y < pitch) val = *reinterpret_cast<const uint4*>(R + (size_t)xr * pitch + y);
+    *reinterpret_cast<uint4*>(&S[row][v * 8]) = val;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x & (TY - 1), half = threadIdx.x / TY;
+  const int y = Y0 + ty;
+  if (y >= NY) return;
+#pragma unroll 1
+  for (int i = 0; i < TX / 2; i++) {
+    const int X = X0 + half * (TX / 2) + i;
+    if (X >= NX) break;
+    if (!SQ && ref_compat && (X == NX - 1 || y == NY - 1 || (y == 0 && X >= 1))) continue;
+    const int sx = X - rlo;
+    const int r0 = S[sx][ty];
+    const bool neg = r0 < 0;
+    int best = r0 * r0;
+    int t = 1;
+    for (; t <= HALO; ++t) {
+      const int tt = t * t;
+      if (tt >= best) break;
+      if (X - t >= 0) {
+        const int r = S[sx - t][ty];
+        best = min(best, tt + (((r < 0) == neg) ? r * r : 0));
+      }
+      if (X + t < NX) {
+        const int r = S[sx + t][ty];
+        best = min(best, tt + (((r < 0) == neg) ? r * r : 0));
+      }
+    }
+    if (t > HALO && t * t < best && (X - t >= 0 || X + t < NX))
+      best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X, y, neg, best, t);
+    if (SQ) {
+      const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
+      pos_sq[(size_t)X * NY + y] = neg ? 0 : v;
+      neg_sq[(size_t)X * NY + y] = neg ? v : 0;
+    } else {
+      dist[(size_t)(X + min_x) * gly + y + min_y] = esdf_value(best, neg, gi);
+    }
+  }
+}
+
+// K2q: the reference's aliased column (ref_compat).  Window-local column 0, rows X = 1..NX-1, is the 1-D
+// transform over the virtual column W(j), j in [1, NX]:  W(j) = R(j, 0) for j <= NX-1, W(NX) = R(NX-1, NY-1),
+// evaluated at j = X  (sdf_map.cpp:639-650: index x*update_Y_SIZE + y with y == update_Y_SIZE aliases row x+1).
+template <bool SQ>
+__global__ void esdf_quirk_col(const int16_t* __restrict__ R, int pitch, int NX, int NY, double* __restrict__ dist, int gly,
+                               int min_x, int min_y, double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  const int X = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (X > NX - 1) return;
+  if (!SQ && X > NX - 2) return;
+  auto W = [&](int j) -> int { return j <= NX - 1 ? R[(size_t)j * pitch] : R[(size_t)(NX - 1) * pitch + (NY - 1)]; };
+  const int r0 = W(X);
+  const bool neg = r0 < 0;
+  int best = r0 * r0;
+  for (int t = 1;; ++t) {
+    const int tt = t * t;
+    if (tt >= best) break;
+    const bool lo_ok = X - t >= 1, hi_ok = X + t <= NX;
+    if (!lo_ok && !hi_ok) break;
+    if (lo_ok) { const int r = W(X - t); best = min(best, tt + (((r < 0) == neg) ? r * r : 0)); }
+    if (hi_ok) { const int r = W(X + t); best = min(best, tt + (((r < 0) == neg) ? r * r : 0)); }
+  }
+  if (SQ) {
+    const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
+    pos_sq[(size_t)X * NY] = neg ? 0 : v;
+    neg_sq[(size_t)X * NY] = neg ? v : 0;
+  } else {
+    dist[(size_t)(X + min_x) * gly + min_y] = esdf_value(best, neg, gi);
+  }
+}
+
+}  // namespace
+
+// Runs K1..K2q on `st`.  d_pos_sq/d_neg_sq != NULL: squared-distance dump of the retained row pass of the
+// last update instead of writing distances (parity tests).
+int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,
+                   int ref_compat, cudaStream_t st, int32_t* d_pos_sq, int32_t* d_neg_sq) {
+  const int NX = max_x - min_x + 1, NY = max_y - min_y + 1;
+  const alore_map_geom_t& g = ctx->geom;
+  if (NX <= 0 || NY <= 0 || min_x < 0 || min_y < 0 || max_x >= g.glx || max_y >= g.gly)
+    return alore_fail(ctx, ALORE_EINVAL, "esdf window [%d,%d]x[%d,%d] outside the %dx%d grid", min_x, max_x, min_y, max_y, g.glx, g.gly);
+  if (NX > 16384 || NY > 16384)
+    return alore_fail(ctx, ALORE_EINVAL, "esdf window %dx%d exceeds the int16/int32 exactness limit 16384", NX, NY);
+  const bool sq = d_pos_sq != nullptr;
+  const int pitch = ((NY + TY - 1) / TY) * TY;
+  const int nblk = (NX + BLK - 1) / BLK;
+  if (!sq) {
+    const size_t need_row = (size_t)NX * pitch, need_blk = (size_t)nblk * pitch;
+    if (need_row > ctx->row_cap) {
+      if (ctx->d_row) cudaFree(ctx->d_row);
+      ctx->d_row = nullptr;
+      ALORE_CUDA(ctx, cudaMalloc(&ctx->d_row, need_row * sizeof(int16_t)));
+      ctx->row_cap = need_row;
+    }
+    if (need_blk > ctx->blk_cap) {
+      if (ctx->d_blk) cudaFree(ctx->d_blk);
+      ctx->d_blk = nullptr;
+      ALORE_CUDA(ctx, cudaMalloc(&ctx->d_blk, need_blk * sizeof(uint32_t)));
+      ctx->blk_cap = need_blk;
+    }
+    ctx->row_pitch = pitch;
+    ctx->win[0] = min_x; ctx->win[1] = min_y; ctx->win[2] = max_x; ctx->win[3] = max_y;
+    ctx->last_ref_compat = ref_compat;
+    const size_t smem = (size_t)(((NY + 31 + 15) >> 4) << 4) + (size_t)NY * 2 + 16;
+    if (smem > 48 * 1024)
+      ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
+    esdf_block_min<<<dim3((NY + 255) / 256, nblk), 256, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
+    ctx->launches += 2;
+  } else if (ctx->row_pitch != pitch || !ctx->d_row) {
+    return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
+  }
+  const dim3 grid((NY + TY - 1) / TY, (NX + TX - 1) / TX);
+  const bool quirk = ref_compat && NX >= 2 && NY >= 2;
+  if (ref_compat && !quirk && !sq) return ALORE_OK;  // update_X_SIZE or update_Y_SIZE == 0: the reference writes nothing
+  if (sq) {
+    esdf_col_pass<true><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                              g.grid_interval, ref_compat, d_pos_sq, d_neg_sq);
+    ctx->launches++;
+    if (quirk) {
+      esdf_quirk_col<true><<<(NX + 127) / 128, 128, 0, st>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                                             g.grid_interval, d_pos_sq, d_neg_sq);
+      ctx->launches++;
+    }
+  } else {
+    esdf_col_pass<false><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                               g.grid_interval, ref_compat, nullptr, nullptr);
+    ctx->launches++;
+    if (quirk && NX >= 3) {
+      esdf_quirk_col<false><<<(NX + 127) / 128, 128, 0, st>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                                              g.grid_interval, nullptr, nullptr);
+      ctx->launches++;
+    }
+  }
+  ALORE_CUDA(ctx, cudaGetLastError());
+  return ALORE_OK;
+}

@@ -1,0 +1,123 @@
+"""GPU parity tests for the ESDF path: CUDA (through the C ABI) vs the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from alore_legged_manipulator_b200 import SDFmap, capi, workloads
+
+pytestmark = pytest.mark.gpu
+DBL_MAX = float(np.finfo(np.float64).max)
+
+
+def make_sdf(ctx, glx, gly, gi, grid, odom=(0.0, 0.0), rng_m=1e6, ref_compat=True):
+    # SDFmap derives GLX = ceil((upper-lower)/gi) like the reference (sdf_map.h:150-151); put the upper
+    # bound half a cell inside the last cell so the ceil is robust to FP rounding of the product
+    xl, yl = -0.5 * glx * gi, -0.5 * gly * gi
+    m = SDFmap(ctx, gridmap_interval=gi, detection_range=rng_m, global_x_lower=xl, global_x_upper=xl + (glx - 0.5) * gi,
+               global_y_lower=yl, global_y_upper=yl + (gly - 0.5) * gi, ref_compat=ref_compat)
+    assert (m.GLX_SIZE_, m.GLY_SIZE_) == (glx, gly)
+    m.gridmap_[:] = grid
+    m.odom_pos_[:2] = odom
+    m.has_map_ = True
+    return m
+
+
+def check_against_oracle(ctx, glx, gly, gi, grid, odom=(0.0, 0.0), rng_m=1e6, check_sq=True):
+    m = make_sdf(ctx, glx, gly, gi, grid, odom, rng_m)
+    m.distance_buffer_all_[:] = -3.0          # sentinel: cells the reference never writes must keep it
+    m.updateESDF2d()
+    mn, mx = m.esdf_window()
+    ref = np.full(glx * gly, -3.0)
+    sp, sn = oracle_lib.esdf_update(m.geom(), m.gridmap_, mn, mx, ref, want_sq=check_sq)
+    assert np.array_equal(m.distance_buffer_all_, ref), "ESDF distances differ from the reference restatement"
+    if check_sq:
+        pos, neg = m.last_squared()
+        NX, NY = mx[0] - mn[0] + 1, mx[1] - mn[1] + 1
+        S = NY - 1
+        if S > 0:
+            # the reference's own buffer index is x*S + y (aliasing stride); compare y < S
+            rp = sp[: NX * S].reshape(NX, S)
+            rn = sn[: NX * S].reshape(NX, S)
+            gp = np.where(pos[:, :S] == capi.ALORE_SQ_INF, DBL_MAX, pos[:, :S].astype(np.float64))
+            gn = np.where(neg[:, :S] == capi.ALORE_SQ_INF, DBL_MAX, neg[:, :S].astype(np.float64))
+            assert np.array_equal(gp, rp), "squared distances (+) differ"
+            assert np.array_equal(gn, rn), "squared distances (-) differ"
+    return m
+
+
+@pytest.mark.parametrize("shape", [(48, 40), (33, 57), (64, 64), (20, 90), (70, 25), (2, 2), (3, 5), (5, 3), (1, 7),
+                                   (200, 200), (130, 257), (257, 130)])
+@pytest.mark.parametrize("dens", [0.0, 1 / 400, 1 / 23, 1 / 3, 1.0])
+def test_small_maps_bit_exact(ctx, shape, dens):
+    glx, gly = shape
+    grid = workloads.random_map(glx, gly, seed=glx * 7 + gly + int(dens * 1000), p_occ=dens, p_unknown=0.05, wall=False)
+    check_against_oracle(ctx, glx, gly, 0.05, grid)
+
+
+def test_sub_window_and_stale_cells(ctx):
+    glx, gly, gi = 300, 260, 0.1
+    grid = workloads.random_map(glx, gly, seed=11, p_occ=0.03)
+    m = check_against_oracle(ctx, glx, gly, gi, grid, odom=(1.3, -2.1), rng_m=6.37)
+    mn, mx = m.esdf_window()
+    assert mn[0] > 0 and mx[1] < gly - 1
+    # second update with a moved window on the same context: cells outside keep the previous values
+    prev = m.distance_buffer_all_.copy()
+    m.odom_pos_[:2] = (-3.0, 2.0)
+    m.gridmap_[:] = workloads.random_map(glx, gly, seed=12, p_occ=0.05)
+    m.updateESDF2d()
+    mn, mx = m.esdf_window()
+    ref = prev.copy()
+    oracle_lib.esdf_update(m.geom(), m.gridmap_, mn, mx, ref)
+    assert np.array_equal(m.distance_buffer_all_, ref)
+
+
+def test_clean_mode_matches_bruteforce(ctx):
+    from test_esdf_oracle import brute_force_expected
+    glx, gly, gi = 48, 40, 0.05
+    grid = workloads.random_map(glx, gly, seed=3, p_occ=0.05, wall=False)
+    m = make_sdf(ctx, glx, gly, gi, grid, ref_compat=False)
+    m.updateESDF2d()
+    exp, _, _, _ = brute_force_expected(grid.reshape(glx, gly), gi, ref_compat=False)
+    assert np.array_equal(m.distance_buffer_all_.reshape(glx, gly), exp)
+
+
+@pytest.mark.parametrize("name", ["bernoulli_0.02", "sparse_1e-4", "dense_0.5", "empty", "single_seed", "corridor",
+                                  "all_occupied"])
+def test_2048_variants_bit_exact(ctx, name):
+    n = 2048
+    if name == "bernoulli_0.02":
+        grid = workloads.random_map(n, n, 2, p_occ=0.02)
+    elif name == "sparse_1e-4":
+        grid = workloads.random_map(n, n, 3, p_occ=1e-4, p_unknown=0.0, wall=False)
+    elif name == "dense_0.5":
+        grid = workloads.random_map(n, n, 4, p_occ=0.5)
+    elif name == "empty":
+        grid = np.full(n * n, capi.UNOCCUPIED, np.uint8)
+    elif name == "single_seed":
+        grid = np.full(n * n, capi.UNOCCUPIED, np.uint8)
+        grid[777 * n + 1300] = capi.OCCUPIED
+    elif name == "corridor":
+        grid = workloads.corridor_map(n, n, 5, width_cells=64)
+    else:
+        grid = np.full(n * n, capi.OCCUPIED, np.uint8)
+    check_against_oracle(ctx, n, n, 0.05, grid)
+
+
+def test_config2_4096_bit_exact(ctx):
+    n = 4096
+    grid = workloads.random_map(n, n, 2, p_occ=0.02, p_unknown=0.01)
+    m = check_against_oracle(ctx, n, n, 0.05, grid, check_sq=False)
+    # size-independent properties on the full map
+    d = m.distance_buffer_all_.reshape(n, n)[: n - 1, : n - 1]
+    occ = grid.reshape(n, n)[: n - 1, : n - 1] == capi.OCCUPIED
+    assert np.all(d[occ] <= 0.0) and np.all(d[~occ] > 0.0)
+    # 1-Lipschitz in grid units between 4-neighbours (exact EDT property, tolerance one ulp-ish)
+    gi = 0.05
+    assert np.max(np.abs(np.diff(d[1:], axis=0))) <= gi * 2 + 1e-12   # sign change adds the +gi offset
+    assert m.last_kernel_ms() > 0.0
+
+
+def test_config5_shape_8192x2048_bit_exact(ctx):
+    glx, gly = 8192, 2048
+    grid = workloads.corridor_map(glx, gly, 5, width_cells=400, clutter=0.02)
+    check_against_oracle(ctx, glx, gly, 0.005, grid, check_sq=False)
