@@ -207,12 +207,15 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.alore_last_error.argtypes = [vp]
     lib.alore_last_error.restype = C.c_char_p
     lib.alore_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.alore_host_register.argtypes = [vp, vp, C.c_size_t]
+    lib.alore_host_unregister.argtypes = [vp, vp]
     lib.alore_params_default.argtypes = [C.POINTER(Params)]
     lib.alore_params_default.restype = None
     lib.alore_esdf_update.argtypes = [vp, C.POINTER(MapGeom), c_uint8_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       c_double_p, C.c_int]
     lib.alore_esdf_update_dev.argtypes = [vp, C.POINTER(MapGeom), vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     lib.alore_esdf_set.argtypes = [vp, C.POINTER(MapGeom), c_double_p]
+    lib.alore_esdf_reset.argtypes = [vp, C.POINTER(MapGeom)]
     lib.alore_esdf_last_sq.argtypes = [vp, c_int32_p, c_int32_p]
     lib.alore_esdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.alore_launch_count.argtypes = [vp]
@@ -242,7 +245,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 # Symbols include/alore_b200.h declares (checked by the CPU test-suite without touching a GPU).
 EXPORTED_SYMBOLS = [
     "alore_create", "alore_destroy", "alore_last_error", "alore_device_info", "alore_params_default",
-    "alore_esdf_update", "alore_esdf_update_dev", "alore_esdf_set", "alore_esdf_last_sq",
+    "alore_host_register", "alore_host_unregister",
+    "alore_esdf_update", "alore_esdf_update_dev", "alore_esdf_set", "alore_esdf_reset", "alore_esdf_last_sq",
     "alore_esdf_last_kernel_ms", "alore_penalty_batch", "alore_penalty_batch_dev", "alore_cost_batch",
     "alore_opt_batch", "alore_batch_upload", "alore_batch_run", "alore_batch_download",
     "alore_batch_device_results", "alore_batch_argmin", "alore_batch_last_kernel_ms", "alore_batch_free",

@@ -6,21 +6,6 @@
 
 static std::string g_create_err;
 
-void alore_pin_host(alore_ctx* ctx, const void* p, size_t bytes) {
-  for (auto& r : ctx->regs)
-    if (r.p == p && r.bytes >= bytes) return;
-  // drop stale registrations of the same base pointer
-  for (size_t i = 0; i < ctx->regs.size(); i++)
-    if (ctx->regs[i].p == p) {
-      cudaHostUnregister(const_cast<void*>(p));
-      ctx->regs.erase(ctx->regs.begin() + i);
-      break;
-    }
-  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
-  if (e == cudaSuccess) ctx->regs.push_back({p, bytes});
-  else (void)cudaGetLastError();  // pageable fallback: copies still work, just slower
-}
-
 extern "C" {
 
 int alore_create(int device, alore_ctx** out) {
@@ -67,6 +52,29 @@ void alore_destroy(alore_ctx* ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int alore_host_register(alore_ctx* ctx, const void* p, size_t bytes) {
+  if (!ctx || !p || !bytes) return ALORE_EINVAL;
+  ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (auto& r : ctx->regs)
+    if (r.p == p) return r.bytes == bytes ? ALORE_OK : alore_fail(ctx, ALORE_EINVAL, "buffer already registered with another size");
+  ALORE_CUDA(ctx, cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault));
+  ctx->regs.push_back({p, bytes});
+  return ALORE_OK;
+}
+
+int alore_host_unregister(alore_ctx* ctx, const void* p) {
+  if (!ctx || !p) return ALORE_EINVAL;
+  for (size_t i = 0; i < ctx->regs.size(); i++)
+    if (ctx->regs[i].p == p) {
+      cudaSetDevice(ctx->device);
+      cudaStreamSynchronize(ctx->stream);
+      cudaHostUnregister(const_cast<void*>(p));
+      ctx->regs.erase(ctx->regs.begin() + i);
+      return ALORE_OK;
+    }
+  return alore_fail(ctx, ALORE_EINVAL, "buffer was not registered");
 }
 
 const char* alore_last_error(const alore_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -121,7 +129,13 @@ void alore_params_default(alore_params_t* p) {
   p->alm_max_outer = 0;
 }
 
-static int ensure_map(alore_ctx* ctx, const alore_map_geom_t* geom) {
+__global__ void fill_f64(double* p, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// (Re)allocates the device grid for `geom`.  A fresh or re-shaped device distance buffer starts at
+// DBL_MAX like SDFmap's constructor (sdf_map.h:160), so device and host agree in never-updated cells.
+static int ensure_map(alore_ctx* ctx, const alore_map_geom_t* geom, bool force_fill = false) {
   if (!geom || geom->glx <= 0 || geom->gly <= 0) return alore_fail(ctx, ALORE_EINVAL, "bad map geometry");
   const size_t cells = (size_t)geom->glx * geom->gly;
   ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -129,12 +143,19 @@ static int ensure_map(alore_ctx* ctx, const alore_map_geom_t* geom) {
     if (ctx->d_occ) cudaFree(ctx->d_occ);
     if (ctx->d_dist) cudaFree(ctx->d_dist);
     ctx->d_occ = nullptr; ctx->d_dist = nullptr; ctx->map_cells = 0;
-    ctx->have_map = false; ctx->dist_host_synced = nullptr;
+    ctx->have_map = false;
     ALORE_CUDA(ctx, cudaMalloc(&ctx->d_occ, cells));
     ALORE_CUDA(ctx, cudaMalloc(&ctx->d_dist, cells * sizeof(double)));
     ctx->map_cells = cells;
+    force_fill = true;
   }
-  if (std::memcmp(&ctx->geom, geom, sizeof(*geom)) != 0) { ctx->geom = *geom; ctx->dist_host_synced = nullptr; }
+  if (std::memcmp(&ctx->geom, geom, sizeof(*geom)) != 0) { ctx->geom = *geom; force_fill = true; }
+  if (force_fill) {
+    fill_f64<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_dist, cells, 1.7976931348623157e308);
+    ctx->launches++;
+    ALORE_CUDA(ctx, cudaGetLastError());
+    ctx->have_map = false;
+  }
   return ALORE_OK;
 }
 
@@ -149,14 +170,6 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
     return alore_fail(ctx, ALORE_EINVAL, "esdf window outside the grid");
   const size_t gly = geom->gly;
   cudaStream_t st = ctx->stream;
-  alore_pin_host(ctx, occ, ctx->map_cells);
-  alore_pin_host(ctx, dist_inout, ctx->map_cells * sizeof(double));
-  // First call on this host buffer: the device copy must agree with the host in the cells the
-  // reference never writes (ctor value DBL_MAX or stale), so upload it once.
-  if (ctx->dist_host_synced != dist_inout) {
-    ALORE_CUDA(ctx, cudaMemcpyAsync(ctx->d_dist, dist_inout, ctx->map_cells * sizeof(double), cudaMemcpyHostToDevice, st));
-    ctx->dist_host_synced = dist_inout;
-  }
   // H2D: the window's rows of the occupancy grid (contiguous chunk).
   ALORE_CUDA(ctx, cudaMemcpyAsync(ctx->d_occ + (size_t)min_x * gly, occ + (size_t)min_x * gly, (size_t)NX * gly,
                                   cudaMemcpyHostToDevice, st));
@@ -195,8 +208,15 @@ int alore_esdf_set(alore_ctx* ctx, const alore_map_geom_t* geom, const double* d
   if (rc) return rc;
   ALORE_CUDA(ctx, cudaMemcpyAsync(ctx->d_dist, dist, ctx->map_cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   ALORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->dist_host_synced = nullptr;
   ctx->have_map = true;
+  return ALORE_OK;
+}
+
+int alore_esdf_reset(alore_ctx* ctx, const alore_map_geom_t* geom) {
+  if (!ctx) return ALORE_EINVAL;
+  int rc = ensure_map(ctx, geom, true);
+  if (rc) return rc;
+  ALORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ALORE_OK;
 }
 

@@ -32,8 +32,7 @@ struct alore_ctx {
   int win[4] = {0, 0, -1, -1};   // min_x, min_y, max_x, max_y of the last update
   int last_ref_compat = 1;
   float esdf_kernel_ms = 0.f;
-  const void* dist_host_synced = nullptr;   // host buffer the device copy mirrors
-  // host buffers registered with cudaHostRegister (pinned for async copies)
+  // host buffers page-locked through alore_host_register (lifetime guaranteed by the caller)
   struct Reg { const void* p; size_t bytes; };
   std::vector<Reg> regs;
 
@@ -58,9 +57,6 @@ inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {
     if (e__ != cudaSuccess)                                                                            \
       return alore_fail((ctx), ALORE_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
   } while (0)
-
-// Pins a caller-owned host buffer once (best effort) so cudaMemcpyAsync runs at PCIe speed.
-void alore_pin_host(alore_ctx* ctx, const void* p, size_t bytes);
 
 // esdf.cu
 int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 
@@ -22,7 +23,7 @@ class SDFmap:
     Unknown, Unoccupied, Occupied = 0, 1, 2  # sdf_map.h:98
 
     def __init__(self, ctx: capi.Context, *, gridmap_interval=0.1, detection_range=5.0, global_x_lower=-10.0,
-                 global_x_upper=10.0, global_y_lower=-10.0, global_y_upper=10.0, ref_compat=True):
+                 global_x_upper=10.0, global_y_lower=-10.0, global_y_upper=10.0, ref_compat=True, pin_host=True):
         # sdf_map.h:120-160
         self.ctx = ctx
         self.grid_interval_ = float(gridmap_interval)
@@ -40,6 +41,25 @@ class SDFmap:
         self.has_esdf_ = False
         self.esdf_need_update_ = False
         self.ref_compat = bool(ref_compat)
+        # The map owns gridmap_ / distance_buffer_all_ for its whole life (like the reference's SDFmap),
+        # so it may page-lock them; released in close() / at garbage collection, before numpy frees them.
+        g = self.geom()
+        ctx.check(ctx.lib.alore_esdf_reset(ctx.h, C.byref(g)))
+        self._pinned = []
+        if pin_host:
+            for a in (self.gridmap_, self.distance_buffer_all_):
+                if ctx.lib.alore_host_register(ctx.h, a.ctypes.data, a.nbytes) == 0:
+                    self._pinned.append(a)
+        self._fin = weakref.finalize(self, SDFmap._release, ctx, list(self._pinned))
+
+    @staticmethod
+    def _release(ctx, arrays):
+        for a in arrays:
+            if ctx.h:
+                ctx.lib.alore_host_unregister(ctx.h, a.ctypes.data)
+
+    def close(self):
+        self._fin()
 
     # ---- geometry ----------------------------------------------------------------------
     def geom(self) -> capi.MapGeom:

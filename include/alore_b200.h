@@ -162,6 +162,13 @@ void alore_destroy(alore_ctx* ctx);
 const char* alore_last_error(const alore_ctx* ctx);     /* ctx may be NULL: last creation error */
 int alore_device_info(const alore_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Optional: page-lock a caller-owned host buffer (SDFmap::gridmap_, distance_buffer_all_) for the
+ * lifetime the CALLER guarantees, so the ESDF copies run at full PCIe speed.  The owner must call
+ * alore_host_unregister before freeing the buffer (SDFmap's destructor, sdf_map.h:186-189).
+ * Unregistered buffers work too (pageable copies, slower). */
+int alore_host_register(alore_ctx* ctx, const void* ptr, size_t bytes);
+int alore_host_unregister(alore_ctx* ctx, const void* ptr);
+
 /* Fills *p with the reference's yaml defaults (global_planning3ms.yaml + plan_tester car3ms.yaml). */
 void alore_params_default(alore_params_t* p);
 
@@ -176,7 +183,8 @@ void alore_params_default(alore_params_t* p);
  * ref_compat 1: reproduce the reference's buffer-aliasing quirks bit for bit;
  *            0: clean EDT over the whole window (last row/col included, no column-0 alias).
  * On return the host mirror is valid AND a device-resident copy of the full distance buffer
- * plus geometry is retained in ctx for the optimizer entry points.
+ * plus geometry is retained in ctx for the optimizer entry points.  The device copy starts at
+ * DBL_MAX (alore_esdf_reset) and then sees exactly the writes the host buffer sees.
  */
 int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* occ,
                       int min_x, int min_y, int max_x, int max_y,
@@ -186,6 +194,11 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
 int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ,
                           int min_x, int min_y, int max_x, int max_y,
                           double* d_dist_inout, int ref_compat, void* cuda_stream);
+
+/* A new SDFmap on this context: (re)allocates the device grid for geom and fills the device
+ * distance buffer with DBL_MAX, the value SDFmap's constructor gives distance_buffer_all_
+ * (sdf_map.h:160), so that device and host agree in cells no update has written yet. */
+int alore_esdf_reset(alore_ctx* ctx, const alore_map_geom_t* geom);
 
 /* Make an existing HOST distance buffer the optimizer's ESDF (uploads it). */
 int alore_esdf_set(alore_ctx* ctx, const alore_map_geom_t* geom, const double* dist);
