@@ -30,6 +30,72 @@
 
 namespace orc {
 
+// TEST HOOK, default off.  The reference pushes a collision sample's position gradient onto the chain of
+// every sample up to AND INCLUDING itself and then weights it with the full-piece Simpson weights
+// (optimizer.cpp:945-946, 1056-1057); the sample's own weight in the partial integral up to its time is
+// 0 (j = 0), 1 (interior even j, where the full-piece weight is 2) or 1 (j = 2K), so the reference's collision
+// gradient is not the exact derivative of its own cost.  With this flag the oracle uses the exact own-weight,
+// which lets tests check EVERY other term of the restatement against finite differences.
+inline bool g_exact_chain_weights = false;
+
+// sin/cos used by the penalty functionals and check_final_collision.  Default: glibc (what the reference
+// calls).  `g_trig_portable`: a self-contained fdlibm-style evaluation (3-term Cody-Waite reduction by pi/2 +
+// the classic degree-13/14 kernels) built only from IEEE +,-,*,/ and floor, so that the CUDA kernels — which
+// carry their own, independently written copy of the same published algorithm — produce the SAME BITS.
+// The reference's optimizer amplifies a 1e-15 input perturbation to percent-level changes of the optimised
+// trajectory (measured), so trajectory-level parity is only meaningful under identical
+// arithmetic; libm-vs-portable differences are <= 1 ulp per call and are reported by the tests.
+inline bool g_trig_portable = false;
+
+namespace ptrig {
+constexpr double invpio2 = 6.36619772367581382433e-01;
+constexpr double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+constexpr double pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21;
+constexpr double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+constexpr double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+inline double ksin(double x, double y) {
+  const double z = x * x;
+  const double v = z * x;
+  const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+  return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+inline double kcos(double x, double y) {
+  const double z = x * x;
+  const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+  const double ax = x < 0.0 ? -x : x;
+  if (ax < 0.3) return 1.0 - (0.5 * z - (z * r - x * y));
+  const double qx = ax > 0.78125 ? 0.28125 : std::floor(0.25 * ax * 4194304.0) / 4194304.0;
+  const double hz = 0.5 * z - qx;
+  const double a = 1.0 - qx;
+  return a - (hz - (z * r - x * y));
+}
+inline void sincos(double x, double& s, double& c) {
+  if (!(x > -1.0e5 && x < 1.0e5)) { s = std::sin(x); c = std::cos(x); return; }
+  const double fn = std::floor(x * invpio2 + 0.5);
+  const int n = (int)fn;
+  // fdlibm __ieee754_rem_pio2, medium-size path, second iteration taken unconditionally (118-bit pi/2):
+  // with |x| < 1e5 the closest any double gets to a multiple of pi/2 still leaves > 60 significant bits.
+  double r = x - fn * pio2_1;
+  const double t = r;
+  double w = fn * pio2_2;
+  r = t - w;
+  w = fn * pio2_2t - ((t - r) - w);
+  const double y0 = r - w;
+  const double y1 = (r - y0) - w;
+  const double ks = ksin(y0, y1), kc = kcos(y0, y1);
+  switch (n & 3) {
+    case 0: s = ks; c = kc; break;
+    case 1: s = kc; c = -ks; break;
+    case 2: s = -ks; c = -kc; break;
+    default: s = -kc; c = ks; break;
+  }
+}
+}  // namespace ptrig
+inline double osin(double x) { if (!g_trig_portable) return std::sin(x); double s, c; ptrig::sincos(x, s, c); return s; }
+inline double ocos(double x) { if (!g_trig_portable) return std::cos(x); double s, c; ptrig::sincos(x, s, c); return c; }
+
 // =====================================================================================
 // E1-E4  grid map + ESDF                                     sdf:453-472, 618-715, 739-871
 // =====================================================================================
@@ -554,7 +620,20 @@ enum {
 };
 
 using Vec = std::vector<double>;
-inline double vdot(const double* a, const double* b, int n) { double s = 0.0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+// Summation order of VectorXd::dot / norm / squaredNorm: NOT defined by the reference's source (Eigen 3.3
+// vectorises it with ISA-dependent packet partial sums).  The oracle fixes it to 32 strided partial sums
+// (element i goes to partial i % 32, in index order) combined by a xor-butterfly (16, 8, 4, 2, 1) — a
+// deterministic order that a 32-lane warp reproduces exactly.
+inline double vdot(const double* a, const double* b, int n) {
+  double p[32], q[32];
+  for (int l = 0; l < 32; l++) p[l] = 0.0;
+  for (int i = 0; i < n; i++) p[i & 31] += a[i] * b[i];
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; l++) q[l] = p[l] + p[l ^ o];
+    for (int l = 0; l < 32; l++) p[l] = q[l];
+  }
+  return p[0];
+}
 inline double vnorm(const double* a, int n) { return std::sqrt(vdot(a, a, n)); }
 inline double vabsmax(const double* a, int n) { double m = std::fabs(a[0]); for (int i = 1; i < n; i++) m = std::max(m, std::fabs(a[i])); return m; }
 
@@ -956,7 +1035,7 @@ struct MSPlanner {
           omgstep = omg * step;
           cTb(i, beta0, sigma); cTb(i, beta1, dsigma); cTb(i, beta2, ddsigma); cTb(i, beta3, dddsigma);
           double gradBeta[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-          double cosyaw = std::cos(sigma[0]), sinyaw = std::sin(sigma[0]);
+          double cosyaw = ocos(sigma[0]), sinyaw = osin(sigma[0]);
           sampleIntegral(j, beta0, beta1, sigma, dsigma, ddsigma, cosyaw, sinyaw, CoeffIntegral, IntegralAlpha, IntegralX, IntegralY, cc);
 
           violaAcc = ddsigma[1] * ddsigma[1] - max_acc_ * max_acc_;
@@ -1063,9 +1142,16 @@ struct MSPlanner {
               cost += omgstep * p.pw_collision * violaPosPena;
             }
           }
-          if (if_coolision) {
+          if (if_coolision && !g_exact_chain_weights) {
             const int cnt = i * S1 + j + 1;
             for (int t = 0; t < cnt; t++) { VecCoeffChainX[t] += all_grad2Pos[0]; VecCoeffChainY[t] += all_grad2Pos[1]; }
+          } else if (if_coolision) {
+            // TEST HOOK (not the reference): exact Simpson weight of the colliding sample itself, see g_exact_chain_weights
+            const int cnt = i * S1 + j;
+            for (int t = 0; t < cnt; t++) { VecCoeffChainX[t] += all_grad2Pos[0]; VecCoeffChainY[t] += all_grad2Pos[1]; }
+            const double ow = (j == 0) ? 0.0 : ((j == SamNumEachPart) ? 1.0 : 0.5);
+            VecCoeffChainX[cnt] += ow * all_grad2Pos[0];
+            VecCoeffChainY[cnt] += ow * all_grad2Pos[1];
           }
           for (int r = 0; r < 6; r++)
             for (int d = 0; d < 2; d++)
@@ -1075,7 +1161,7 @@ struct MSPlanner {
           s1 += halfstep;
           IntegralAlpha = 1.0 / SamNumEachPart * j;
           cTb(i, beta0, sigma); cTb(i, beta1, dsigma); cTb(i, beta2, ddsigma);
-          double cosyaw = std::cos(sigma[0]), sinyaw = std::sin(sigma[0]);
+          double cosyaw = ocos(sigma[0]), sinyaw = osin(sigma[0]);
           sampleIntegral(j, beta0, beta1, sigma, dsigma, ddsigma, cosyaw, sinyaw, CoeffIntegral, IntegralAlpha, IntegralX, IntegralY, cc);
         }
       }
@@ -1133,7 +1219,7 @@ struct MSPlanner {
           IntegralAlpha = 1.0 / SamNumEachPart * j;
           omg = (j == 0 || j == SamNumEachPart) ? 0.5 : 1;
           cTb(i, beta0, sigma); cTb(i, beta1, dsigma); cTb(i, beta2, ddsigma); cTb(i, beta3, dddsigma);
-          double cosyaw = std::cos(sigma[0]), sinyaw = std::sin(sigma[0]);
+          double cosyaw = ocos(sigma[0]), sinyaw = osin(sigma[0]);
           sampleIntegral(j, beta0, beta1, sigma, dsigma, ddsigma, cosyaw, sinyaw, CoeffIntegral, IntegralAlpha, IntegralX, IntegralY, cc);
           double gradViolaMt;
           double Alpha = 1.0 / sparseResolution_ * (double(j) / 2);
@@ -1185,7 +1271,7 @@ struct MSPlanner {
           s1 += halfstep;
           IntegralAlpha = 1.0 / SamNumEachPart * j;
           cTb(i, beta0, sigma); cTb(i, beta1, dsigma); cTb(i, beta2, ddsigma);
-          double cosyaw = std::cos(sigma[0]), sinyaw = std::sin(sigma[0]);
+          double cosyaw = ocos(sigma[0]), sinyaw = osin(sigma[0]);
           sampleIntegral(j, beta0, beta1, sigma, dsigma, ddsigma, cosyaw, sinyaw, CoeffIntegral, IntegralAlpha, IntegralX, IntegralY, cc);
         }
       }
@@ -1362,19 +1448,19 @@ struct MSPlanner {
         if (p.if_standard_diff) {
           if (j % 2 == 0) {
             if (j != 0) {
-              IntegralX[j / 2 - 1] += CoeffIntegral * currVel[1] * std::cos(currPos[0]);
-              IntegralY[j / 2 - 1] += CoeffIntegral * currVel[1] * std::sin(currPos[0]);
+              IntegralX[j / 2 - 1] += CoeffIntegral * currVel[1] * ocos(currPos[0]);
+              IntegralY[j / 2 - 1] += CoeffIntegral * currVel[1] * osin(currPos[0]);
             }
             if (j != SamNum) {
-              IntegralX[j / 2] += CoeffIntegral * currVel[1] * std::cos(currPos[0]);
-              IntegralY[j / 2] += CoeffIntegral * currVel[1] * std::sin(currPos[0]);
+              IntegralX[j / 2] += CoeffIntegral * currVel[1] * ocos(currPos[0]);
+              IntegralY[j / 2] += CoeffIntegral * currVel[1] * osin(currPos[0]);
             }
           } else {
-            IntegralX[j / 2] += 4.0 * CoeffIntegral * currVel[1] * std::cos(currPos[0]);
-            IntegralY[j / 2] += 4.0 * CoeffIntegral * currVel[1] * std::sin(currPos[0]);
+            IntegralX[j / 2] += 4.0 * CoeffIntegral * currVel[1] * ocos(currPos[0]);
+            IntegralY[j / 2] += 4.0 * CoeffIntegral * currVel[1] * osin(currPos[0]);
           }
         } else {
-          double cosyaw = std::cos(currPos[0]), sinyaw = std::sin(currPos[0]);
+          double cosyaw = ocos(currPos[0]), sinyaw = osin(currPos[0]);
           if (j % 2 == 0) {
             if (j != 0) {
               IntegralX[j / 2 - 1] += CoeffIntegral * (currVel[1] * cosyaw + currVel[0] * icr * sinyaw);

@@ -330,6 +330,14 @@ int orc_frontend_make(int n_path, const double* path_xy, const double* start_xyt
   return N;
 }
 
+void orc_set_exact_chain_weights(int on) { orc::g_exact_chain_weights = on != 0; }
+
+void orc_set_trig_portable(int on) { orc::g_trig_portable = on != 0; }
+void orc_sincos(double x, int portable, double* s, double* c) {
+  if (portable) orc::ptrig::sincos(x, *s, *c);
+  else { *s = std::sin(x); *c = std::cos(x); }
+}
+
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"
