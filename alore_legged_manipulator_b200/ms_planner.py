@@ -74,6 +74,7 @@ class MSPlanner:
         return bool(res.ok[0])
 
     def minco_plan_batch(self, cands: capi.CandidateBatch) -> capi.ResultBatch:
+        self.map_._check_owner()
         res = capi.ResultBatch(cands)
         cs, rs = cands.as_struct(), res.as_struct()
         self.ctx.check(self.ctx.lib.alore_opt_batch(self.ctx.h, C.byref(self.params), C.byref(cs), C.byref(rs)))
@@ -107,6 +108,7 @@ class MSPlanner:
     def cost_batch(self, cands: capi.CandidateBatch, stage: int, x: np.ndarray, lam=None, rho=None, safe_dis=None,
                    g_init=None):
         """One costFunctionCallback (stage 1) / costFunctionCallbackPath (stage 0) per candidate."""
+        self.map_._check_owner()
         B = cands.B
         x = np.ascontiguousarray(x, dtype=np.float64)
         assert x.size == cands.n_vars()
@@ -122,6 +124,7 @@ class MSPlanner:
 
     def penalty_batch(self, piece_off, coeffs, piece_T, start_xy, final_xy):
         """attachPenaltyFunctional on given coefficients (BASELINE config 3)."""
+        self.map_._check_owner()
         piece_off = np.ascontiguousarray(piece_off, dtype=np.int32)
         B, tot = piece_off.size - 1, int(piece_off[-1])
         cost, gC, gT, err = np.zeros(B), np.zeros((tot, 6, 2)), np.zeros(tot), np.zeros((B, 2))

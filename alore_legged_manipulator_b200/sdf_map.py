@@ -45,6 +45,7 @@ class SDFmap:
         # so it may page-lock them; released in close() / at garbage collection, before numpy frees them.
         g = self.geom()
         ctx.check(ctx.lib.alore_esdf_reset(ctx.h, C.byref(g)))
+        ctx.map_owner = weakref.ref(self)      # one alore_ctx holds ONE device-resident grid map
         self._pinned = []
         if pin_host:
             for a in (self.gridmap_, self.distance_buffer_all_):
@@ -99,6 +100,11 @@ class SDFmap:
         return self.gridmap_[self.Index2Vectornum(ix, iy)] == self.Occupied
 
     # ---- ESDF -----------------------------------------------------------------------------
+    def _check_owner(self):
+        owner = getattr(self.ctx, "map_owner", None)
+        if owner is None or owner() is not self:
+            raise capi.AloreError("this Context's device map now belongs to another SDFmap (one context = one map)")
+
     def esdf_window(self):
         """min_esdf / max_esdf exactly as sdf_map.cpp:619-621 computes them (FP, then truncation)."""
         ox, oy = float(self.odom_pos_[0]), float(self.odom_pos_[1])
@@ -110,6 +116,7 @@ class SDFmap:
         return mn, mx
 
     def updateESDF2d(self):  # sdf_map.cpp:618-680 -> alore_esdf_update
+        self._check_owner()
         mn, mx = self.esdf_window()
         g = self.geom()
         rc = self.ctx.lib.alore_esdf_update(self.ctx.h, C.byref(g), capi.u8ptr(self.gridmap_), mn[0], mn[1], mx[0],
