@@ -233,6 +233,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         lib.alore_batch_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         lib.alore_batch_argmin.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         lib.alore_batch_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        lib.alore_batch_stats.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         lib.alore_batch_free.argtypes = [vp]
         lib.alore_batch_free.restype = None
         lib.alore_final_collision_batch.argtypes = [vp, C.POINTER(Params), C.c_int, c_int32_p, c_double_p, c_double_p,
@@ -249,7 +250,7 @@ EXPORTED_SYMBOLS = [
     "alore_esdf_update", "alore_esdf_update_dev", "alore_esdf_set", "alore_esdf_reset", "alore_esdf_last_sq",
     "alore_esdf_last_kernel_ms", "alore_penalty_batch", "alore_penalty_batch_dev", "alore_cost_batch",
     "alore_opt_batch", "alore_batch_upload", "alore_batch_run", "alore_batch_download",
-    "alore_batch_device_results", "alore_batch_argmin", "alore_batch_last_kernel_ms", "alore_batch_free",
+    "alore_batch_device_results", "alore_batch_argmin", "alore_batch_last_kernel_ms", "alore_batch_stats", "alore_batch_free",
     "alore_final_collision_batch", "alore_launch_count",
 ]
 

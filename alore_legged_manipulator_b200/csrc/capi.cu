@@ -193,12 +193,23 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
 int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ, int min_x, int min_y,
                           int max_x, int max_y, double* d_dist_inout, int ref_compat, void* cuda_stream) {
   if (!ctx) return ALORE_EINVAL;
-  if (!d_occ || !d_dist_inout) return alore_fail(ctx, ALORE_EINVAL, "null buffer");
   if (!geom || geom->glx <= 0 || geom->gly <= 0) return alore_fail(ctx, ALORE_EINVAL, "bad map geometry");
   ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool resident = (d_occ == nullptr && d_dist_inout == nullptr);
+  if (resident) {
+    // HBM-resident path: rebuild the context's own ESDF from the occupancy grid a previous alore_esdf_update left on the device
+    if (!ctx->d_occ || !ctx->d_dist || (size_t)geom->glx * geom->gly != ctx->map_cells)
+      return alore_fail(ctx, ALORE_ENOMAP, "no resident occupancy grid of this geometry: call alore_esdf_update first");
+    d_occ = ctx->d_occ;
+    d_dist_inout = ctx->d_dist;
+  } else if (!d_occ || !d_dist_inout) {
+    return alore_fail(ctx, ALORE_EINVAL, "pass both device buffers, or neither to use the context's resident map");
+  }
   ctx->geom = *geom;
-  return alore_esdf_run(ctx, d_occ, d_dist_inout, min_x, min_y, max_x, max_y, ref_compat, (cudaStream_t)cuda_stream,
-                        nullptr, nullptr);
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  int rc = alore_esdf_run(ctx, d_occ, d_dist_inout, min_x, min_y, max_x, max_y, ref_compat, st, nullptr, nullptr);
+  if (rc == ALORE_OK && resident) ctx->have_map = true;
+  return rc;
 }
 
 int alore_esdf_set(alore_ctx* ctx, const alore_map_geom_t* geom, const double* dist) {

@@ -37,6 +37,8 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, int 
   w.nterm = reinterpret_cast<int*>(slab + L.nterm); w.rank = reinterpret_cast<int*>(slab + L.rank);
   w.TS = L.TS; w.tsum = 0.0;
   w.evals = 0;
+  w.iters = 0;
+  w.alg_bytes = 0.0;
   w.err[0] = w.err[1] = 0.0;
 }
 
@@ -138,6 +140,8 @@ __device__ void minco_plan(Warp& w, const KParams& kp, const BatchDev& bt, int b
     out.evals[b] = w.evals;
     out.cost[b] = cost;
     out.tail_s[b] = w.x[2 * (N - 1)];
+    out.alg_bytes[b] = w.alg_bytes;
+    out.iters[b] = w.iters;
   }
   double* oi = out.inner_pts + 2 * (size_t)(p0 - b);
   for (int i = lane; i < 2 * (N - 1); i += 32) oi[i] = w.x[i];
@@ -401,6 +405,7 @@ int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch*
   UP(r.ok, nul_i, B) UP(r.status, nul_i, B) UP(r.replans, nul_i, B) UP(r.alm_iters, nul_i, B) UP(r.evals, nul_i, B)
   UP(r.cost, nul_d, B) UP(r.inner_pts, nul_d, 2 * (size_t)(tot - B)) UP(r.tail_s, nul_d, B) UP(r.piece_T, nul_d, tot)
   UP(r.coeffs, nul_d, 12 * (size_t)tot)
+  UP(r.alg_bytes, nul_d, B) UP(r.iters, nul_i, B)
   UP(bh->d_best, nul_d, 1) UP(bh->d_best_idx, nul_i, 1)
 #undef UP
   cudaEventCreate(&bh->e0);
@@ -462,6 +467,23 @@ int alore_batch_argmin(alore_ctx* ctx, alore_batch* bh, double* best_cost, int32
   ALORE_CUDA(ctx, cudaStreamSynchronize(st));
   if (best_cost) *best_cost = bc;
   if (best_idx) *best_idx = bi;
+  return ALORE_OK;
+}
+
+int alore_batch_stats(alore_ctx* ctx, alore_batch* bh, double* alg_bytes, long long* evals, long long* iters) {
+  if (!ctx || !bh) return ALORE_EINVAL;
+  ALORE_CUDA(ctx, cudaDeviceSynchronize());
+  std::vector<double> hb(bh->B);
+  std::vector<int> hi(bh->B), he(bh->B);
+  ALORE_CUDA(ctx, cudaMemcpy(hb.data(), bh->res.alg_bytes, bh->B * sizeof(double), cudaMemcpyDeviceToHost));
+  ALORE_CUDA(ctx, cudaMemcpy(hi.data(), bh->res.iters, bh->B * sizeof(int), cudaMemcpyDeviceToHost));
+  ALORE_CUDA(ctx, cudaMemcpy(he.data(), bh->res.evals, bh->B * sizeof(int), cudaMemcpyDeviceToHost));
+  double sb = 0.0;
+  long long si = 0, se = 0;
+  for (int b = 0; b < bh->B; b++) { sb += hb[b]; si += hi[b]; se += he[b]; }
+  if (alg_bytes) *alg_bytes = sb;
+  if (iters) *iters = si;
+  if (evals) *evals = se;
   return ALORE_OK;
 }
 

@@ -45,6 +45,12 @@ class DeviceBatch:
         self.ctx.check(self.ctx.lib.alore_batch_device_results(self.h, C.byref(dc), C.byref(dk)))
         return dc.value, dk.value
 
+    def stats(self):
+        """(algorithmic bytes, cost evaluations, L-BFGS iterations) summed over the batch of the last run."""
+        ab, ev, it = C.c_double(), C.c_longlong(), C.c_longlong()
+        self.ctx.check(self.ctx.lib.alore_batch_stats(self.ctx.h, self.h, C.byref(ab), C.byref(ev), C.byref(it)))
+        return float(ab.value), int(ev.value), int(it.value)
+
     def kernel_ms(self) -> float:
         ms = C.c_float()
         self.ctx.check(self.ctx.lib.alore_batch_last_kernel_ms(self.h, C.byref(ms)))

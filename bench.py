@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of the planning_ddr_opt hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One STEP = one replan tick of one rank: rebuild the ESDF of the 2048x2048 map from its occupancy grid, then
+run MSPlanner::minco_plan (stage A L-BFGS + stage B augmented-Lagrangian L-BFGS loop + final collision
+check with replans) on the rank's block of candidate trajectories, find the best candidate on the device
+and (N>1) all-gather (best cost, index) over NCCL.
+
+Workload (BASELINE.json configs[3] family, weak scaling anchored at its 8-GPU point): 65 way-points
+(32 chairs + 32 targets + start) on a 2048^2 @0.05 m map -> 4160 ordered legs x 4 goal headings = 16 640
+candidates built by the front-end time allocation; rank r optimises candidates [2080 r, 2080 (r+1)), so the
+8-GPU job is exactly the ~16k-candidate batch of configs[3].  The ESDF of BASELINE configs[1] (4096^2) is timed
+separately in the same run and reported under "esdf".
+
+Prints ONE JSON line (rank 0).  `value` = candidates optimised per second, inputs resident in HBM, device time
+(CUDA events), max over ranks.  `e2e` = the same through the host-buffer C ABI (alore_esdf_update +
+alore_opt_batch) with every copy inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+PER_GPU = 2080
+METRIC = "candidate trajs optimized/sec (ESDF Mcells/s under 'esdf')"
+UNIT = "trajs/s"
+
+
+def build_world(seed=4):
+    """configs[3]: 2048^2 map, 65 points, all ordered legs x 4 headings (deterministic)."""
+    from alore_legged_manipulator_b200 import workloads
+    n = 2048
+    grid = workloads.random_map(n, n, seed, p_occ=0.0, p_unknown=0.0, wall=True, boxes=400, box_cells=(6, 30))
+    geom = workloads.make_geom(n, n, 0.05)
+    return geom, grid
+
+
+def build_candidates(geom, grid, dist, lo, hi, seed=4):
+    from alore_legged_manipulator_b200 import front_end, workloads
+    pts = workloads.free_points(grid, geom, dist, 65, seed, min_clear=0.9)
+    headings = (0.0, math.pi / 2, math.pi, 3 * math.pi / 2)
+    fts = []
+    idx = 0
+    for h in headings:                       # heading-major so every block of 2080 spans all leg lengths
+        for i in range(65):
+            for j in range(65):
+                if i == j:
+                    continue
+                if lo <= idx < hi:
+                    a, b = pts[i], pts[j]
+                    fts.append(front_end.make_flat_traj([tuple(a), tuple(b)], (a[0], a[1], 0.0), (b[0], b[1], h)))
+                idx += 1
+    return front_end.pack_candidates(fts)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the real one needs ROS+Eigen+PCL and
+    cannot be built here) on all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib
+    from alore_legged_manipulator_b200 import capi
+    lib = oracle_lib.load()
+    cores = int(lib.orc_hardware_threads()) or os.cpu_count() or 1
+    geom, grid = build_world()
+    dist = np.full(geom.glx * geom.gly, np.finfo(np.float64).max)
+    oracle_lib.esdf_update(geom, grid, (0, 0), (geom.glx - 1, geom.gly - 1), dist)
+    cands = build_candidates(geom, grid, dist, 0, PER_GPU)
+    prm = capi.default_params()
+    t_esdf, t_opt = [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle_lib.esdf_update(geom, grid, (0, 0), (geom.glx - 1, geom.gly - 1), dist)
+        t1 = time.perf_counter()
+        res = oracle_lib.opt_batch(prm, geom, dist, cands, cores)
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            t_esdf.append(t1 - t0)
+            t_opt.append(t2 - t1)
+    total = sum(t_esdf) + sum(t_opt)
+    val = cands.B * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[3] family: ESDF 2048^2 rebuild + minco_plan of {cands.B} candidates (rank-0 block) per step",
+                   "pieces_mean": float(np.diff(cands.piece_off).mean()), "threads": cores},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"the full rank-0 block ({cands.B} candidates) + one single-thread 2048^2 ESDF per step"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "esdf_s_per_step": float(np.mean(t_esdf)), "opt_s_per_step": float(np.mean(t_opt)),
+        "ok_fraction": float(res.ok.mean()),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--per-gpu", type=int, default=PER_GPU)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import alore_legged_manipulator_b200 as alore
+    from alore_legged_manipulator_b200 import capi, sharding, workloads
+    from alore_legged_manipulator_b200.ms_planner import DeviceBatch, MSPlanner
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()          # a real (non-NULL) stream so that CUDA events bracket our kernels
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    ctx = alore.Context(local)
+    prm = alore.default_params()
+    peak, peak_src = measured_peak()
+
+    # ---- ESDF of BASELINE configs[1]: 4096^2, kernel-only (HBM-resident) and end to end ---------------------
+    esdf_info = {}
+    if rank == 0:
+        n2 = 4096
+        g2 = workloads.make_geom(n2, n2, 0.05)
+        grid2 = workloads.random_map(n2, n2, 2, p_occ=0.02, p_unknown=0.01)
+        m2 = alore.SDFmap(ctx, gridmap_interval=0.05, detection_range=1e6, global_x_lower=g2.x_lower,
+                          global_x_upper=g2.x_lower + (n2 - 0.5) * 0.05, global_y_lower=g2.y_lower,
+                          global_y_upper=g2.y_lower + (n2 - 0.5) * 0.05)
+        m2.gridmap_[:] = grid2
+        m2.has_map_ = True
+        e2e_t = []
+        for it in range(6):
+            t0 = time.perf_counter()
+            m2.updateESDF2d()
+            e2e_t.append(time.perf_counter() - t0)
+        gg = m2.geom()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        for a, b in evs:
+            flush.fill_(1)                                    # L2 flush between timed iterations
+            a.record(stream)
+            ctx.check(ctx.lib.alore_esdf_update_dev(ctx.h, C.byref(gg), None, 0, 0, n2 - 1, n2 - 1, None, 1, sptr))
+            b.record(stream)
+        torch.cuda.synchronize()
+        ks = sorted(a.elapsed_time(b) for a, b in evs)
+        k_ms = float(np.median(ks))
+        cells = n2 * n2
+        esdf_info = {"workload": "configs[1]: 4096x4096, Bernoulli(0.02) occupied + 1% unknown + wall, full-map window",
+                     "kernel_ms": k_ms, "mcells_per_s": cells / k_ms / 1e3,
+                     "roofline": {"bound": "hbm", "achieved": 13 * cells / k_ms / 1e6, "peak": peak, "unit": "GB/s",
+                                  "frac": 13 * cells / k_ms / 1e6 / peak, "bytes_per_cell": 13},
+                     "e2e_ms": 1e3 * min(e2e_t[1:]), "e2e_mcells_per_s": cells / min(e2e_t[1:]) / 1e6,
+                     "l2_flush_between_iterations": True}
+        del flush
+        m2.close()
+        del m2
+
+    # ---- candidate workload ----------------------------------------------------------------------------------
+    geom, grid = build_world()
+    m = alore.SDFmap(ctx, gridmap_interval=0.05, detection_range=1e6, global_x_lower=geom.x_lower,
+                     global_x_upper=geom.x_lower + (geom.glx - 0.5) * 0.05, global_y_lower=geom.y_lower,
+                     global_y_upper=geom.y_lower + (geom.gly - 0.5) * 0.05)
+    m.gridmap_[:] = grid
+    m.has_map_ = True
+    m.forceUpdateESDF()                                        # also leaves the occupancy grid resident
+    gm = m.geom()
+    lo, hi = sharding.shard_range(rank, world, per_rank=args.per_gpu)
+    cands = build_candidates(gm, grid, m.distance_buffer_all_, lo, hi)
+    pl = MSPlanner(ctx, prm, m)
+    db = DeviceBatch(ctx, cands)
+
+    def step_resident():
+        ctx.check(ctx.lib.alore_esdf_update_dev(ctx.h, C.byref(gm), None, 0, 0, geom.glx - 1, geom.gly - 1, None, 1, sptr))
+        db.run(prm, sptr)
+        bc, bi = db.argmin()                                   # on-device argmin of this rank's block
+        # the only exchange: all-gather of (best cost, global index) per rank over NCCL
+        return sharding.gather_best(bc, lo + bi if bi >= 0 else -1, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        kern_ms.append(db.kernel_ms())
+    e1.record(stream)
+    barrier()
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    alg_bytes, evals, iters = db.stats()
+    res = db.download()
+
+    # ---- end to end through the host-buffer C ABI ---------------------------------------------------------------
+    def step_e2e():
+        m.updateESDF2d()
+        r = pl.minco_plan_batch(cands)
+        sharding.gather_best(*sharding.local_best(r.cost, r.ok, lo), device="cuda")
+        return r
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(cands.B), float(cands.total_pieces), alg_bytes, float(evals), float(iters), float(launches)],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    total_B = int(tot[0])
+
+    if rank == 0:
+        value = total_B * args.steps / (dev_ms / 1e3)
+        e2e_val = total_B * args.steps / (e2e_ms / 1e3)
+        k_avg = float(np.mean(kern_ms))
+        cells = geom.glx * geom.gly
+        h2d = cells + sum(a.nbytes for a in (cands.piece_off, cands.inner_pts, cands.init_T, cands.inner_init_pos,
+                                              cands.start_state, cands.final_state, cands.start_xytheta,
+                                              cands.final_xytheta, cands.if_cut))
+        d2h = 8 * (geom.glx - 1) * (geom.gly - 1) + sum(a.nbytes for a in (res.ok, res.status, res.replans, res.alm_iters,
+                                                                           res.evals, res.cost, res.inner_pts, res.tail_s,
+                                                                           res.piece_T, res.coeffs))
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("opt_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[3] family: per step and per GPU, ESDF 2048^2 rebuild + minco_plan of {args.per_gpu} "
+                                   f"candidates (block r of the 16 640 = 4160 legs x 4 headings; 8 GPUs = the full ~16k batch)",
+                       "candidates_total": total_B, "pieces_mean": float(tot[1]) / total_B, "sparseResolution": int(prm.sparseResolution),
+                       "lbfgs_mem_size": int(prm.lbfgs.mem_size), "parallelism": f"candidate-sharded x{world}, ESDF replicated",
+                       "l2": "working set (per-warp L-BFGS history + scratch, > 1 GB) is larger than L2; no flush needed"},
+            "roofline": {"bound": "hbm", "kernel": "opt_kernel", "achieved": float(tot[2]) / world / (k_avg / 1e3) / 1e9,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": float(tot[2]) / world / (k_avg / 1e3) / 1e9 / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": float(tot[2]) / world, "kernel_ms_per_launch": k_avg,
+                         "note": "FP64-latency/issue bound, not HBM bound: see DESIGN.md section 6"},
+            "esdf": esdf_info,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(tot[5]),
+            "clocks": clocks,
+            "work": {"cost_evals_per_step": float(tot[3]), "lbfgs_iterations_per_step": float(tot[4]),
+                     "ok_fraction": float(res.ok.mean())},
+        }
+        if world == 1 and not args.skip_cpu_baseline:
+            sys.path.insert(0, str(ROOT / "tests"))
+            import oracle_lib
+            lib = oracle_lib.load()
+            cores = int(lib.orc_hardware_threads()) or os.cpu_count() or 1
+            t0 = time.perf_counter()
+            ref = oracle_lib.opt_batch(prm, gm, m.distance_buffer_all_, cands, cores)
+            dt = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            scratch = m.distance_buffer_all_.copy()
+            oracle_lib.esdf_update(gm, grid, (0, 0), (geom.glx - 1, geom.gly - 1), scratch)
+            dte = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cands.B / (dt + dte), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"one full step on the host: single-thread 2048^2 ESDF ({dte:.2f} s) + the rank-0 block "
+                                              f"of {cands.B} candidates on {cores} threads ({dt:.2f} s)",
+                                    "esdf_mcells_per_s_1thread": cells / dte / 1e6}
+        print(json.dumps(line), flush=True)
+    db.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -190,7 +190,9 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
                       int min_x, int min_y, int max_x, int max_y,
                       double* dist_inout, int ref_compat);
 
-/* Same, with occ and dist already in device memory (HBM-resident path used for kernel timing). */
+/* Same, with occ and dist already in device memory (HBM-resident path used for kernel timing),
+ * asynchronous on cuda_stream.  d_occ == NULL and d_dist_inout == NULL: rebuild the context's own
+ * resident ESDF from the occupancy grid the last alore_esdf_update left on the device. */
 int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ,
                           int min_x, int min_y, int max_x, int max_y,
                           double* d_dist_inout, int ref_compat, void* cuda_stream);
@@ -260,6 +262,9 @@ int alore_batch_download(alore_ctx* ctx, alore_batch* batch, alore_results_t* ou
 int alore_batch_device_results(alore_batch* batch, const double** d_cost, const int32_t** d_ok);
 /* Best (lowest final cost among ok candidates) of the last run: computed on the device. */
 int alore_batch_argmin(alore_ctx* ctx, alore_batch* batch, double* best_cost, int32_t* best_idx);
+/* Totals over the batch of the last run: algorithmic bytes (per evaluation
+ * 8*(2n+1) + 32*C*N*(K+1) [stage 1], per L-BFGS update 8*n*(4*bound+4)), cost evaluations, L-BFGS iterations. */
+int alore_batch_stats(alore_ctx* ctx, alore_batch* batch, double* alg_bytes, long long* evals, long long* iters);
 /* Device time (ms) of the optimisation kernel(s) of the last alore_batch_run / alore_opt_batch. */
 int alore_batch_last_kernel_ms(const alore_batch* batch, float* ms);
 void alore_batch_free(alore_batch* batch);
