@@ -330,6 +330,38 @@ int orc_frontend_make(int n_path, const double* path_xy, const double* start_xyt
   return N;
 }
 
+// The three analytic problems of oracle/ref_lbfgs_capi.cpp through the ORACLE's lbfgs_optimize (same callbacks).
+int orc_lbfgs_run(int kind, int n, double* x, const alore_lbfgs_params_t* param, double* f, int* evals) {
+  Vec xx(x, x + n);
+  int ev = 0;
+  auto fn = [&](const Vec& v, Vec& g) {
+    ev++;
+    double fx = 0.0;
+    if (kind == 0) {
+      for (int i = 0; i < n; i += 2) {
+        double t1 = 1.0 - v[i];
+        double t2 = 10.0 * (v[i + 1] - v[i] * v[i]);
+        g[i + 1] = 20.0 * t2;
+        g[i] = -2.0 * (v[i] * g[i + 1] + t1);
+        fx += t1 * t1 + t2 * t2;
+      }
+    } else {
+      for (int i = 0; i < n; i++) {
+        const double w = 1.0 + 50.0 * i;
+        const double a = v[i] - 0.1 * i;
+        fx += 0.5 * w * a * a + (kind == 1 ? std::fabs(v[i]) : 0.0);
+        g[i] = w * a + (kind == 1 ? (v[i] > 0 ? 1.0 : -1.0) : 0.0);
+      }
+      if (kind == 2 && v[0] > 3.0) return 1.0 / 0.0;
+    }
+    return fx;
+  };
+  int ret = lbfgs_optimize(xx, *f, fn, *param);
+  std::memcpy(x, xx.data(), n * sizeof(double));
+  if (evals) *evals = ev;
+  return ret;
+}
+
 void orc_set_exact_chain_weights(int on) { orc::g_exact_chain_weights = on != 0; }
 
 void orc_set_trig_portable(int on) { orc::g_trig_portable = on != 0; }

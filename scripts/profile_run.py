@@ -1,0 +1,41 @@
+"""Small, fixed workloads for ncu captures (one process, one GPU):  esdf | penalty | opt"""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np
+import alore_legged_manipulator_b200 as alore
+from alore_legged_manipulator_b200 import workloads, capi
+from alore_legged_manipulator_b200.ms_planner import MSPlanner, DeviceBatch
+from test_esdf_gpu import make_sdf
+
+which = sys.argv[1]
+ctx = alore.Context(0)
+prm = alore.default_params()
+if which == "esdf":
+    n = 4096
+    grid = workloads.random_map(n, n, 2, p_occ=0.02, p_unknown=0.01)
+    m = make_sdf(ctx, n, n, 0.05, grid)
+    for _ in range(3):
+        m.updateESDF2d()
+    print("esdf kernels ms", m.last_kernel_ms())
+else:
+    n = 2048
+    grid = workloads.random_map(n, n, 3, p_occ=0.0, p_unknown=0.0, wall=True, boxes=400, box_cells=(6, 30))
+    m = make_sdf(ctx, n, n, 0.05, grid)
+    m.updateESDF2d()
+    pl = MSPlanner(ctx, prm, m)
+    if which == "penalty":
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+        po, coeffs, T, s_xy, f_xy = workloads.random_spline_batch(B, 64, m.geom(), m.distance_buffer_all_, grid, seed=3)
+        for _ in range(2):
+            c, gC, gT, err = pl.penalty_batch(po, coeffs, T, s_xy, f_xy)
+        print("penalty done", float(c.mean()))
+    else:
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+        pts = workloads.free_points(grid, m.geom(), m.distance_buffer_all_, 40, 4, min_clear=0.9)
+        legs = workloads.leg_candidates(pts, headings=(0.0,), max_legs=B)
+        db = DeviceBatch(ctx, legs)
+        db.run(prm)
+        r = db.download()
+        print("opt done: kernel ms", db.kernel_ms(), "ok", int(r.ok.sum()), "evals", int(r.evals.sum()))
