@@ -23,15 +23,19 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, int 
   w.N = N; w.n = 3 * N - 1; w.n6 = 6 * N; w.K = K; w.S1 = 2 * K + 1;
   const int Nm = L.Nmax;
   double* s = smem;
-  w.cf = s; s += 12 * Nm;
-  w.gC = s; s += 12 * Nm;
   w.T1 = s; s += Nm; w.T2 = s; s += Nm; w.T3 = s; s += Nm; w.T4 = s; s += Nm; w.T5 = s; s += Nm;
   w.gT = s; s += Nm;
   w.pXY = s; s += 2 * (Nm + 1);
-  w.sumT = s;
+  w.sumT = s; s += Nm + 1 + 3;
+  w.ring = s; s += 208;
+  w.ringb = s; s += 32;
+  w.stg = s; s += 272;
+  w.stgb = s;
+  w.Nm = Nm;
+  w.cf = slab + L.cf; w.gC = slab + L.gC;
   w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp; w.d = slab + L.d;
   w.lm_s = slab + L.lm_s; w.lm_y = slab + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys;
-  w.pf = slab + L.pf; w.Ab = slab + L.Ab; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
+  w.pf = slab + L.pf; w.Uf = slab + L.Ab; w.Lf = slab + L.Ab + (size_t)7 * 6 * Nm; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
   w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
   w.terms = slab + L.terms; w.cg = slab + L.cg; w.fold = slab + L.fold;
   w.nterm = reinterpret_cast<int*>(slab + L.nterm); w.rank = reinterpret_cast<int*>(slab + L.rank);
@@ -79,9 +83,8 @@ __device__ void coefficients_from_x(Warp& w) {
     w.T2[i] = t2; w.T3[i] = t2 * T; w.T4[i] = t2 * t2; w.T5[i] = (t2 * t2) * T;
   }
   __syncwarp();
-  minco_assemble(w, w.x);
-  band_lu(w.Ab, w.n6, lane);
-  band_solve(w.Ab, w.n6, lane, w.gC, w.cf);
+  minco_lu_forward(w, w.x);
+  minco_back(w);
 }
 
 // MSPlanner::minco_plan for candidate b                                       optimizer.cpp:169-220
@@ -156,7 +159,10 @@ __device__ __forceinline__ int next_job(int* counter, int lane) {
   return __shfl_sync(FULL, j, 0);
 }
 
-__global__ void __launch_bounds__(32)
+#ifndef ALORE_OPT_MINBLOCKS
+#define ALORE_OPT_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(32, ALORE_OPT_MINBLOCKS)
 opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, double* slabs, int* counter) {
   extern __shared__ __align__(16) double smem[];
   double* slab = slabs + (size_t)blockIdx.x * kp.L.total;

@@ -31,6 +31,25 @@ else:
         for _ in range(2):
             c, gC, gT, err = pl.penalty_batch(po, coeffs, T, s_xy, f_xy)
         print("penalty done", float(c.mean()))
+    elif which == "cost":
+        # B copies of one ~64-piece leg: one full cost+gradient evaluation per warp (stage 1 then stage 0)
+        import oracle_lib
+        from alore_legged_manipulator_b200 import front_end
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 1184
+        pts = workloads.free_points(grid, m.geom(), m.distance_buffer_all_, 40, 4, min_clear=0.9)
+        best = None
+        for i in range(40):
+            for j in range(40):
+                if i != j:
+                    ft = front_end.make_flat_traj([tuple(pts[i]), tuple(pts[j])], (pts[i][0], pts[i][1], 0.0), (pts[j][0], pts[j][1], 1.0))
+                    if best is None or abs(ft.TrajNum - 64) < abs(best.TrajNum - 64):
+                        best = ft
+        print("pieces", best.TrajNum)
+        cands = front_end.pack_candidates([best] * B)
+        x = np.tile(oracle_lib.initial_x(cands, 0), B)
+        for stage in (1, 0, 1):
+            c, g, e = pl.cost_batch(cands, stage, x)
+        print("cost done", c[0])
     else:
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
         pts = workloads.free_points(grid, m.geom(), m.distance_buffer_all_, 40, 4, min_clear=0.9)
