@@ -139,6 +139,91 @@ esdf_row_pass(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int mi
   for (int y = (nv << 3) + threadIdx.x; y < NY; y += ROW_THREADS) dst[y] = s_d[y];
 }
 
+// K1 (fast path): rows that start on a 16-byte boundary.  Each thread owns GP consecutive groups of 16 cells;
+// a group is one 16-byte load turned into two 16-bit masks (Occupied / not Occupied), nearest seeds inside the
+// group come from clz/ffs on the masks, nearest seeds outside from block-wide scans of per-thread extremes.
+constexpr int ROW_GP_MAX = 8;
+__device__ __forceinline__ unsigned occ_mask4(unsigned w) {   // 4 cells -> 4 bits (bit i = byte i == Occupied)
+  const unsigned e = __vcmpeq4(w, 0x02020202u) & 0x01010101u;
+  return (e & 1u) | ((e >> 7) & 2u) | ((e >> 14) & 4u) | ((e >> 21) & 8u);
+}
+__global__ void __launch_bounds__(ROW_THREADS)
+esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int min_x, int min_y, int NX, int NY,
+                int16_t* __restrict__ R, int pitch, int GP) {
+  __shared__ int s_warp[ROW_THREADS / 32];
+  const int X = blockIdx.x;
+  const size_t row0 = (size_t)(X + min_x) * gly + min_y;
+  const int G = (NY + 15) >> 4;
+  const int g0 = threadIdx.x * GP;
+  unsigned om[ROW_GP_MAX], fm[ROW_GP_MAX];
+  const int BIG = 1 << 20;
+  int lastOcc = -BIG, lastFree = -BIG, firstOcc = BIG, firstFree = BIG;
+#pragma unroll
+  for (int q = 0; q < ROW_GP_MAX; q++) {
+    om[q] = 0u; fm[q] = 0u;
+    const int g = g0 + q;
+    if (q < GP && g < G) {
+      const size_t off = row0 + (size_t)g * 16;
+      uint4 v;
+      if (off + 16 <= occ_total) v = *reinterpret_cast<const uint4*>(occ + off);
+      else {
+        __align__(16) unsigned char b[16];
+        for (int t = 0; t < 16; t++) b[t] = (off + t < occ_total) ? occ[off + t] : 0;
+        v = *reinterpret_cast<uint4*>(b);
+      }
+      const unsigned o = occ_mask4(v.x) | (occ_mask4(v.y) << 4) | (occ_mask4(v.z) << 8) | (occ_mask4(v.w) << 12);
+      const int rem = NY - g * 16;
+      const unsigned valid = rem >= 16 ? 0xffffu : ((1u << rem) - 1u);
+      om[q] = o & valid;
+      fm[q] = ~o & valid;
+      if (om[q]) { lastOcc = g * 16 + 31 - __clz(om[q]); if (firstOcc == BIG) firstOcc = g * 16 + __ffs(om[q]) - 1; }
+      if (fm[q]) { lastFree = g * 16 + 31 - __clz(fm[q]); if (firstFree == BIG) firstFree = g * 16 + __ffs(fm[q]) - 1; }
+    }
+  }
+  int lo = excl_scan_max(lastOcc, s_warp, -BIG);
+  int lf = excl_scan_max(lastFree, s_warp, -BIG);
+  const int no = excl_scan_min_rev(firstOcc, s_warp, BIG);
+  const int nf = excl_scan_min_rev(firstFree, s_warp, BIG);
+  // nearest seed to the right of each owned group (suffix over the thread's own groups)
+  int ro[ROW_GP_MAX], rf[ROW_GP_MAX];
+  {
+    int co = no, cf = nf;
+#pragma unroll
+    for (int q = ROW_GP_MAX - 1; q >= 0; q--) {
+      ro[q] = co; rf[q] = cf;
+      const int g = g0 + q;
+      if (om[q]) co = g * 16 + __ffs(om[q]) - 1;
+      if (fm[q]) cf = g * 16 + __ffs(fm[q]) - 1;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < ROW_GP_MAX; q++) {
+    const int g = g0 + q;
+    if (q < GP && g < G) {
+      unsigned outw[8];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int y = g * 16 + i;
+        const bool isocc = (om[q] >> i) & 1u;
+        const unsigned m = isocc ? fm[q] : om[q];           // seeds of the OTHER kind
+        const unsigned below = m & ((1u << i) - 1u), above = m >> (i + 1);
+        const int left = below ? g * 16 + 31 - __clz(below) : (isocc ? lf : lo);
+        const int right = above ? y + __ffs(above) : (isocc ? rf[q] : ro[q]);
+        const int d = min(min(y - left, right - y), SENT);
+        const int v = isocc ? -d : d;
+        if (i & 1) outw[i >> 1] |= ((unsigned)v & 0xffffu) << 16;
+        else outw[i >> 1] = (unsigned)v & 0xffffu;
+      }
+      int16_t* dst = R + (size_t)X * pitch + g * 16;
+      reinterpret_cast<uint4*>(dst)[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+      reinterpret_cast<uint4*>(dst)[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+      // carries for the next owned group
+      if (om[q]) lo = g * 16 + 31 - __clz(om[q]);
+      if (fm[q]) lf = g * 16 + 31 - __clz(fm[q]);
+    }
+  }
+}
+
 // K1b: block minima for far-search pruning.  grid (ceil(NY/256), ceil(NX/BLK)).
 __global__ void esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,14 +266,27 @@ __device__ __noinline__ int esdf_far_search(const int16_t* __restrict__ R, int p
   return best;
 }
 
+// sqrt(k) for k < SQRT_TBL, filled once per process by esdf_fill_sqrt_table with the device's own sqrt.rn.f64
+// (so looking a value up is bit-identical to computing it); most squared distances of a cluttered map are small.
+constexpr int SQRT_TBL = 4096;
+__device__ double g_sqrt_tbl[SQRT_TBL];
+__global__ void esdf_fill_sqrt_table() {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < SQRT_TBL) g_sqrt_tbl[k] = sqrt((double)k);
+}
+
 __device__ __forceinline__ double esdf_value(int best, bool neg, double gi) {
-  const double root = (best >= SQ_SENT) ? sqrt(DBL_MAX) : sqrt((double)best);
+  double root;
+  if (best < SQRT_TBL) root = g_sqrt_tbl[best];
+  else root = (best >= SQ_SENT) ? sqrt(DBL_MAX) : sqrt((double)best);
   const double dv = __dmul_rn(gi, root);               // grid_interval_ * std::sqrt(val)
   return neg ? __dadd_rn(0.0, __dadd_rn(-dv, gi))      // all = pos(=0); all += (-neg + gi)
              : dv;
 }
 
 // K2: column pass.  grid (ceil(NY/TY), ceil(NX/TX)), 256 threads = 128 columns x 2 row halves.
+// A probe of row x' contributes t^2 + g(x')^2 where g is the row distance of the SAME kind as the query cell
+// (0 for the other kind): g = max(sgn * R, 0) with sgn = +1 for free/unknown query cells, -1 for occupied ones.
 template <bool SQ>
 __global__ void __launch_bounds__(256)
 esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
@@ -208,26 +306,34 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   const int ty = threadIdx.x & (TY - 1), half = threadIdx.x / TY;
   const int y = Y0 + ty;
   if (y >= NY) return;
+  const bool interior = (rlo >= 0) && (X0 + TX + HALO <= NX);   // every probed row of this tile exists
+  const int Xb = X0 + half * (TX / 2);
+  const int Xe = min(Xb + TX / 2, NX);
+  double* out = dist + (size_t)(Xb + min_x) * gly + y + min_y;
+  const bool skip_col = !SQ && ref_compat && (y == NY - 1);
 #pragma unroll 1
-  for (int i = 0; i < TX / 2; i++) {
-    const int X = X0 + half * (TX / 2) + i;
-    if (X >= NX) break;
-    if (!SQ && ref_compat && (X == NX - 1 || y == NY - 1 || (y == 0 && X >= 1))) continue;
+  for (int X = Xb; X < Xe; X++, out += gly) {
+    if (!SQ && ref_compat && (skip_col || X == NX - 1 || (y == 0 && X >= 1))) continue;
     const int sx = X - rlo;
-    const int r0 = S[sx][ty];
+    const int16_t* col = &S[sx][ty];
+    const int r0 = col[0];
     const bool neg = r0 < 0;
+    const int sgn = neg ? -1 : 1;
     int best = r0 * r0;
     int t = 1;
-    for (; t <= HALO; ++t) {
-      const int tt = t * t;
-      if (tt >= best) break;
-      if (X - t >= 0) {
-        const int r = S[sx - t][ty];
-        best = min(best, tt + (((r < 0) == neg) ? r * r : 0));
+    if (interior) {
+      for (; t <= HALO; ++t) {
+        const int tt = t * t;
+        if (tt >= best) break;
+        const int a = max(sgn * (int)col[-t * TY], 0), b = max(sgn * (int)col[t * TY], 0);
+        best = min(best, min(a * a, b * b) + tt);
       }
-      if (X + t < NX) {
-        const int r = S[sx + t][ty];
-        best = min(best, tt + (((r < 0) == neg) ? r * r : 0));
+    } else {
+      for (; t <= HALO; ++t) {
+        const int tt = t * t;
+        if (tt >= best) break;
+        if (X - t >= 0) { const int a = max(sgn * (int)col[-t * TY], 0); best = min(best, a * a + tt); }
+        if (X + t < NX) { const int b = max(sgn * (int)col[t * TY], 0); best = min(best, b * b + tt); }
       }
     }
     if (t > HALO && t * t < best && (X - t >= 0 || X + t < NX))
@@ -237,7 +343,7 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
       pos_sq[(size_t)X * NY + y] = neg ? 0 : v;
       neg_sq[(size_t)X * NY + y] = neg ? v : 0;
     } else {
-      dist[(size_t)(X + min_x) * gly + y + min_y] = esdf_value(best, neg, gi);
+      *out = esdf_value(best, neg, gi);
     }
   }
 }
@@ -285,6 +391,15 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
   if (NX > 16384 || NY > 16384)
     return alore_fail(ctx, ALORE_EINVAL, "esdf window %dx%d exceeds the int16/int32 exactness limit 16384", NX, NY);
   const bool sq = d_pos_sq != nullptr;
+  {
+    static bool tbl_ready[64] = {false};
+    if (ctx->device < 64 && !tbl_ready[ctx->device]) {
+      esdf_fill_sqrt_table<<<SQRT_TBL / 256, 256, 0, st>>>();
+      ALORE_CUDA(ctx, cudaStreamSynchronize(st));   // other streams / contexts may use the table next
+      ctx->launches++;
+      tbl_ready[ctx->device] = true;
+    }
+  }
   const int pitch = ((NY + TY - 1) / TY) * TY;
   const int nblk = (NX + BLK - 1) / BLK;
   if (!sq) {
@@ -307,7 +422,13 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
     const size_t smem = (size_t)(((NY + 31 + 15) >> 4) << 4) + (size_t)NY * 2 + 16;
     if (smem > 48 * 1024)
       ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
+    const int G16 = (NY + 15) / 16;
+    const int GP = (G16 + ROW_THREADS - 1) / ROW_THREADS;
+    const bool fast = (((uintptr_t)d_occ & 15) == 0) && (g.gly % 16 == 0) && (min_y % 16 == 0) && GP <= ROW_GP_MAX;
+    if (fast)
+      esdf_row_pass16<<<NX, ROW_THREADS, 0, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch, GP);
+    else
+      esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     esdf_block_min<<<dim3((NY + 255) / 256, nblk), 256, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
     ctx->launches += 2;
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
