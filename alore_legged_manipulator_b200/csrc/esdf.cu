@@ -147,22 +147,23 @@ __device__ __forceinline__ unsigned occ_mask4(unsigned w) {   // 4 cells -> 4 bi
   const unsigned e = __vcmpeq4(w, 0x02020202u) & 0x01010101u;
   return (e & 1u) | ((e >> 7) & 2u) | ((e >> 14) & 4u) | ((e >> 21) & 8u);
 }
+template <int GP>
 __global__ void __launch_bounds__(ROW_THREADS)
 esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int min_x, int min_y, int NX, int NY,
-                int16_t* __restrict__ R, int pitch, int GP) {
+                int16_t* __restrict__ R, int pitch) {
   __shared__ int s_warp[ROW_THREADS / 32];
   const int X = blockIdx.x;
   const size_t row0 = (size_t)(X + min_x) * gly + min_y;
   const int G = (NY + 15) >> 4;
   const int g0 = threadIdx.x * GP;
-  unsigned om[ROW_GP_MAX], fm[ROW_GP_MAX];
+  unsigned om[GP], fm[GP];
   const int BIG = 1 << 20;
   int lastOcc = -BIG, lastFree = -BIG, firstOcc = BIG, firstFree = BIG;
 #pragma unroll
-  for (int q = 0; q < ROW_GP_MAX; q++) {
+  for (int q = 0; q < GP; q++) {
     om[q] = 0u; fm[q] = 0u;
     const int g = g0 + q;
-    if (q < GP && g < G) {
+    if (g < G) {
       const size_t off = row0 + (size_t)g * 16;
       uint4 v;
       if (off + 16 <= occ_total) v = *reinterpret_cast<const uint4*>(occ + off);
@@ -185,11 +186,11 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
   const int no = excl_scan_min_rev(firstOcc, s_warp, BIG);
   const int nf = excl_scan_min_rev(firstFree, s_warp, BIG);
   // nearest seed to the right of each owned group (suffix over the thread's own groups)
-  int ro[ROW_GP_MAX], rf[ROW_GP_MAX];
+  int ro[GP], rf[GP];
   {
     int co = no, cf = nf;
 #pragma unroll
-    for (int q = ROW_GP_MAX - 1; q >= 0; q--) {
+    for (int q = GP - 1; q >= 0; q--) {
       ro[q] = co; rf[q] = cf;
       const int g = g0 + q;
       if (om[q]) co = g * 16 + __ffs(om[q]) - 1;
@@ -197,29 +198,42 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
     }
   }
 #pragma unroll
-  for (int q = 0; q < ROW_GP_MAX; q++) {
+  for (int q = 0; q < GP; q++) {
     const int g = g0 + q;
-    if (q < GP && g < G) {
-      unsigned outw[8];
+    if (g < G) {
+      // four running-distance recurrences over the 16 cells (nearest Occupied / nearest free, from the left / right)
+      const int y0 = g * 16;
+      int dl_o[16], dl_f[16];
+      {
+        int eo = y0 - 1 - lo, ef = y0 - 1 - lf;     // distance of cell -1 to the nearest seed on its left
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const int y = g * 16 + i;
-        const bool isocc = (om[q] >> i) & 1u;
-        const unsigned m = isocc ? fm[q] : om[q];           // seeds of the OTHER kind
-        const unsigned below = m & ((1u << i) - 1u), above = m >> (i + 1);
-        const int left = below ? g * 16 + 31 - __clz(below) : (isocc ? lf : lo);
-        const int right = above ? y + __ffs(above) : (isocc ? rf[q] : ro[q]);
-        const int d = min(min(y - left, right - y), SENT);
-        const int v = isocc ? -d : d;
-        if (i & 1) outw[i >> 1] |= ((unsigned)v & 0xffffu) << 16;
-        else outw[i >> 1] = (unsigned)v & 0xffffu;
+        for (int i = 0; i < 16; i++) {
+          eo = ((om[q] >> i) & 1u) ? 0 : eo + 1;
+          ef = ((fm[q] >> i) & 1u) ? 0 : ef + 1;
+          dl_o[i] = eo;
+          dl_f[i] = ef;
+        }
       }
-      int16_t* dst = R + (size_t)X * pitch + g * 16;
+      unsigned outw[8];
+      {
+        int eo = ro[q] - (y0 + 16), ef = rf[q] - (y0 + 16);   // distance of cell 16 to the nearest seed on its right
+#pragma unroll
+        for (int i = 15; i >= 0; i--) {
+          const bool isocc = (om[q] >> i) & 1u;
+          eo = isocc ? 0 : eo + 1;
+          ef = ((fm[q] >> i) & 1u) ? 0 : ef + 1;
+          const int d = min(isocc ? min(dl_f[i], ef) : min(dl_o[i], eo), SENT);   // seeds of the OTHER kind
+          const int v = isocc ? -d : d;
+          if (i & 1) outw[i >> 1] = ((unsigned)v & 0xffffu) << 16;
+          else outw[i >> 1] |= (unsigned)v & 0xffffu;
+        }
+      }
+      int16_t* dst = R + (size_t)X * pitch + y0;
       reinterpret_cast<uint4*>(dst)[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
       reinterpret_cast<uint4*>(dst)[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
       // carries for the next owned group
-      if (om[q]) lo = g * 16 + 31 - __clz(om[q]);
-      if (fm[q]) lf = g * 16 + 31 - __clz(fm[q]);
+      if (om[q]) lo = y0 + 31 - __clz(om[q]);
+      if (fm[q]) lf = y0 + 31 - __clz(fm[q]);
     }
   }
 }
@@ -425,8 +439,15 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
     const int G16 = (NY + 15) / 16;
     const int GP = (G16 + ROW_THREADS - 1) / ROW_THREADS;
     const bool fast = (((uintptr_t)d_occ & 15) == 0) && (g.gly % 16 == 0) && (min_y % 16 == 0) && GP <= ROW_GP_MAX;
-    if (fast)
-      esdf_row_pass16<<<NX, ROW_THREADS, 0, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch, GP);
+    const size_t occ_total = (size_t)g.glx * g.gly;
+    if (fast && GP <= 1)
+      esdf_row_pass16<1><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
+    else if (fast && GP <= 2)
+      esdf_row_pass16<2><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
+    else if (fast && GP <= 4)
+      esdf_row_pass16<4><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
+    else if (fast)
+      esdf_row_pass16<8><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     else
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     esdf_block_min<<<dim3((NY + 255) / 256, nblk), 256, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);

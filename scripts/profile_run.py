@@ -21,7 +21,7 @@ if which == "esdf":
     print("esdf kernels ms", m.last_kernel_ms())
 else:
     n = 2048
-    grid = workloads.random_map(n, n, 3, p_occ=0.0, p_unknown=0.0, wall=True, boxes=400, box_cells=(6, 30))
+    grid = workloads.random_map(n, n, 4 if which == "bench" else 3, p_occ=0.0, p_unknown=0.0, wall=True, boxes=400, box_cells=(6, 30))
     m = make_sdf(ctx, n, n, 0.05, grid)
     m.updateESDF2d()
     pl = MSPlanner(ctx, prm, m)
@@ -50,6 +50,15 @@ else:
         for stage in (1, 0, 1):
             c, g, e = pl.cost_batch(cands, stage, x)
         print("cost done", c[0])
+    elif which == "bench":
+        # the exact per-GPU candidate block of bench.py (rank 0), one optimisation launch
+        import bench
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else bench.PER_GPU
+        cands = bench.build_candidates(m.geom(), grid, m.distance_buffer_all_, 0, B)
+        db = DeviceBatch(ctx, cands)
+        db.run(prm)
+        r = db.download()
+        print("bench block done: kernel ms", db.kernel_ms(), "ok", int(r.ok.sum()), "evals", int(r.evals.sum()), "alg bytes", db.stats()[0])
     else:
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
         pts = workloads.free_points(grid, m.geom(), m.distance_buffer_all_, 40, 4, min_clear=0.9)
