@@ -48,6 +48,7 @@ void alore_destroy(alore_ctx* ctx) {
   if (ctx->d_row) cudaFree(ctx->d_row);
   if (ctx->d_blk) cudaFree(ctx->d_blk);
   if (ctx->opt_scratch) cudaFree(ctx->opt_scratch);
+  if (ctx->opt_hist) cudaFree(ctx->opt_hist);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

@@ -39,6 +39,8 @@ struct alore_ctx {
   // ---- optimizer scratch (see traj_opt.cu) ----
   void* opt_scratch = nullptr;
   size_t opt_scratch_bytes = 0;
+  void* opt_hist = nullptr;      // L-BFGS history ring of every resident warp
+  size_t opt_hist_bytes = 0;
 };
 
 inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {

@@ -18,7 +18,7 @@ struct KParams {
   int mcap;
 };
 
-__device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, int N, int K) {
+__device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, double* hist, int N, int K) {
   w.lane = threadIdx.x & 31;
   w.N = N; w.n = 3 * N - 1; w.n6 = 6 * N; w.K = K; w.S1 = 2 * K + 1;
   const int Nm = L.Nmax;
@@ -34,7 +34,7 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, int 
   w.Nm = Nm;
   w.cf = slab + L.cf; w.gC = slab + L.gC;
   w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp; w.d = slab + L.d;
-  w.lm_s = slab + L.lm_s; w.lm_y = slab + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys;
+  w.lm_s = hist + L.lm_s; w.lm_y = hist + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys;
   w.pf = slab + L.pf; w.Uf = slab + L.Ab; w.Lf = slab + L.Ab + (size_t)7 * 6 * Nm; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
   w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
   w.terms = slab + L.terms; w.cg = slab + L.cg; w.fold = slab + L.fold;
@@ -163,9 +163,10 @@ __device__ __forceinline__ int next_job(int* counter, int lane) {
 #define ALORE_OPT_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(32, ALORE_OPT_MINBLOCKS)
-opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, double* slabs, int* counter) {
+opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, double* slabs, double* hists, int* counter) {
   extern __shared__ __align__(16) double smem[];
   double* slab = slabs + (size_t)blockIdx.x * kp.L.total;
+  double* hist = hists + (size_t)blockIdx.x * kp.L.hist_total;
   const int lane = threadIdx.x & 31;
   for (;;) {
     const int job = next_job(counter, lane);
@@ -173,7 +174,7 @@ opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, doubl
     const int b = bt.order ? bt.order[job] : job;
     const int N = bt.piece_off[b + 1] - bt.piece_off[b];
     Warp w;
-    carve(w, kp.L, smem, slab, N, kp.P.sparseResolution);
+    carve(w, kp.L, smem, slab, hist, N, kp.P.sparseResolution);
     minco_plan(w, kp, bt, b, out);
   }
 }
@@ -191,7 +192,7 @@ cost_kernel(const __grid_constant__ KParams kp, BatchDev bt, int stage, const do
     const int p0 = bt.piece_off[b];
     const int N = bt.piece_off[b + 1] - p0;
     Warp w;
-    carve(w, kp.L, smem, slab, N, kp.P.sparseResolution);
+    carve(w, kp.L, smem, slab, slab, N, kp.P.sparseResolution);
     load_candidate(w, bt, b, p0);
     for (int d = 0; d < 2; d++) {
       w.lam[d] = lam ? lam[2 * b + d] : kp.P.EqualLambda[d];
@@ -226,7 +227,7 @@ penalty_kernel(const __grid_constant__ KParams kp, int B, const int* piece_off, 
     const int p0 = piece_off[b];
     const int N = piece_off[b + 1] - p0;
     Warp w;
-    carve(w, kp.L, smem, slab, N, kp.P.sparseResolution);
+    carve(w, kp.L, smem, slab, slab, N, kp.P.sparseResolution);
     w.sx = start_xy[2 * b]; w.sy = start_xy[2 * b + 1];
     w.fx = final_xy[2 * b]; w.fy = final_xy[2 * b + 1];
     for (int d = 0; d < 2; d++) { w.lam[d] = kp.P.EqualLambda[d]; w.rho[d] = kp.P.EqualRho[d]; }
@@ -257,7 +258,7 @@ collision_kernel(const __grid_constant__ KParams kp, int B, const int* piece_off
     const int p0 = piece_off[b];
     const int N = piece_off[b + 1] - p0;
     Warp w;
-    carve(w, kp.L, smem, slab, N, kp.P.sparseResolution);
+    carve(w, kp.L, smem, slab, slab, N, kp.P.sparseResolution);
     w.sx = start_xy[2 * b]; w.sy = start_xy[2 * b + 1];
     const double* c = coeffs + 12 * (size_t)p0;
     for (int i = lane; i < 12 * N; i += 32) w.cf[i] = c[i];
@@ -301,6 +302,7 @@ struct Launch {
   int slots = 0;
   size_t smem = 0;
   double* slabs = nullptr;
+  double* hists = nullptr;
   int* counter = nullptr;
 };
 
@@ -333,7 +335,36 @@ int prepare_launch(alore_ctx* ctx, const alore_params_t* prm, int Nmax, int B, K
   }
   L.counter = reinterpret_cast<int*>(ctx->opt_scratch);
   L.slabs = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->opt_scratch) + 256);
+  if (need_history) {
+    const size_t hneed = (size_t)L.slots * L.kp.L.hist_total * sizeof(double);
+    if (hneed > ctx->opt_hist_bytes) {
+      if (ctx->opt_hist) cudaFree(ctx->opt_hist);
+      ctx->opt_hist = nullptr; ctx->opt_hist_bytes = 0;
+      ALORE_CUDA(ctx, cudaMalloc(&ctx->opt_hist, hneed));
+      ctx->opt_hist_bytes = hneed;
+    }
+    L.hists = reinterpret_cast<double*>(ctx->opt_hist);
+  }
   return ALORE_OK;
+}
+
+// Ask L2 to keep the per-warp evaluation scratch (factors, coefficients, sin/cos, ...) resident while the L-BFGS
+// history — touched once per iteration, ~1 MB per warp — streams through (it would otherwise evict the scratch).
+void set_l2_window(alore_ctx* ctx, cudaStream_t st, void* base, size_t bytes) {
+  static int max_persist = -1, max_window = -1;
+  if (max_persist < 0) {
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+  }
+  if (max_persist <= 0 || max_window <= 0) return;
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.base_ptr = base;
+  v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)std::max<size_t>(v.accessPolicyWindow.num_bytes, 1));
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) (void)cudaGetLastError();
 }
 
 template <typename T>
@@ -429,7 +460,8 @@ int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, 
   if (rc) return rc;
   ALORE_CUDA(ctx, cudaMemsetAsync(L.counter, 0, sizeof(int), st));
   ALORE_CUDA(ctx, cudaEventRecord(bh->e0, st));
-  opt_kernel<<<L.slots, 32, L.smem, st>>>(L.kp, bh->bt, bh->res, L.slabs, L.counter);
+  set_l2_window(ctx, st, L.slabs, (size_t)L.slots * L.kp.L.total * sizeof(double));
+  opt_kernel<<<L.slots, 32, L.smem, st>>>(L.kp, bh->bt, bh->res, L.slabs, L.hists, L.counter);
   ctx->launches++;
   ALORE_CUDA(ctx, cudaGetLastError());
   ALORE_CUDA(ctx, cudaEventRecord(bh->e1, st));

@@ -56,7 +56,8 @@ def build_candidates(geom, grid, dist, lo, hi, seed=4):
     """Candidates [lo, hi) of the deterministic enumeration (variant-major so that every block spans all leg lengths):
     variant v = 0..15 -> goal heading (v % 8) * pi/4, start heading (v // 8) * pi/2; then i -> j over the 65 points."""
     from alore_legged_manipulator_b200 import front_end, workloads
-    pts = workloads.free_points(grid, geom, dist, 65, seed, min_clear=0.9)
+    # way-points inside the central 50 m x 50 m of the 102 m map: leg lengths give TrajNum = 3 .. ~80 (SURVEY.md section 8d, config 4)
+    pts = workloads.free_points(grid, geom, dist, 65, seed, min_clear=0.9, margin_m=26.0)
     fts = []
     idx = 0
     for v in range(16):
