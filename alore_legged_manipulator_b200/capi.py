@@ -12,7 +12,8 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libalore_b200.so"
+# ALORE_B200_LIB: developer override used by the tuning scripts to A/B differently compiled builds of the same sources
+LIB_PATH = Path(os.environ.get("ALORE_B200_LIB") or (PKG_DIR / "libalore_b200.so"))
 
 ALORE_MAX_CHECKPOINTS = 8
 ALORE_SQ_INF = 0x7FFFFFFF
@@ -238,6 +239,9 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         lib.alore_batch_free.restype = None
         lib.alore_final_collision_batch.argtypes = [vp, C.POINTER(Params), C.c_int, c_int32_p, c_double_p, c_double_p,
                                                     c_double_p, c_int32_p, c_double_p]
+        lib.alore_debug_force_exact_division.argtypes = [vp, C.c_int]
+        lib.alore_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong), C.c_int]
+        lib.alore_selftest_division.argtypes = [vp, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
     if path is None:
         _lib = lib
     return lib
@@ -251,7 +255,7 @@ EXPORTED_SYMBOLS = [
     "alore_esdf_last_kernel_ms", "alore_penalty_batch", "alore_penalty_batch_dev", "alore_cost_batch",
     "alore_opt_batch", "alore_batch_upload", "alore_batch_run", "alore_batch_download",
     "alore_batch_device_results", "alore_batch_argmin", "alore_batch_last_kernel_ms", "alore_batch_stats", "alore_batch_free",
-    "alore_final_collision_batch", "alore_launch_count",
+    "alore_final_collision_batch", "alore_selftest_division", "alore_debug_force_exact_division", "alore_debug_phase_cycles", "alore_launch_count",
 ]
 
 

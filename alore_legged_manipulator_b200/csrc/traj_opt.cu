@@ -27,15 +27,15 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, doub
   w.gT = s; s += Nm;
   w.pXY = s; s += 2 * (Nm + 1);
   w.sumT = s; s += Nm + 1 + 3;
-  w.ring = s; s += 208;
-  w.ringb = s; s += 32;
-  w.stg = s; s += 272;
+  s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s) + 15) & ~uintptr_t(15));   // stg/stgb are accessed as double2
+  w.ring = s; s += 384;
+  w.stg = s; s += 304;
   w.stgb = s;
   w.Nm = Nm;
   w.cf = slab + L.cf; w.gC = slab + L.gC;
   w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp; w.d = slab + L.d;
   w.lm_s = hist + L.lm_s; w.lm_y = hist + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys;
-  w.pf = slab + L.pf; w.Uf = slab + L.Ab; w.Lf = slab + L.Ab + (size_t)7 * 6 * Nm; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
+  w.pf = slab + L.pf; w.Uf = slab + L.Ab; w.Lf = slab + L.Ab + (size_t)8 * 6 * Nm; w.zb = slab + L.zb; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
   w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
   w.terms = slab + L.terms; w.cg = slab + L.cg; w.fold = slab + L.fold;
   w.nterm = reinterpret_cast<int*>(slab + L.nterm); w.rank = reinterpret_cast<int*>(slab + L.rank);
@@ -294,6 +294,38 @@ __global__ void argmin_kernel(int B, const double* cost, const int* ok, double* 
   if (threadIdx.x == 0) { *best_cost = sc[0]; *best_idx = si[0]; }
 }
 
+// Self-test of the division split (traj_opt.cuh: rcp_refine / div_rcp) against the compiler's own a / b.
+// Operand pairs come from a counter-based generator: mode 0 = raw 64-bit patterns (every exponent, NaN/Inf/subnormal
+// included), mode 1 = magnitudes 2^-40 .. 2^40 (what the banded solves see), mode 2 = near-equal mantissas.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void division_selftest_kernel(long long n, unsigned long long seed, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long ra = mix64(seed + 2 * (unsigned long long)i), rb = mix64(seed + 2 * (unsigned long long)i + 1);
+    double a, b;
+    const int mode = (int)(i % 3);
+    if (mode == 0) {
+      a = __longlong_as_double((long long)ra);
+      b = __longlong_as_double((long long)rb);
+    } else {
+      const unsigned long long ma = ra & 0x000fffffffffffffull, mb = mode == 2 ? (ma ^ (rb & 0xffull)) : (rb & 0x000fffffffffffffull);
+      const unsigned long long ea = 1023 - 40 + ((ra >> 52) % 81), eb = 1023 - 40 + ((rb >> 52) % 81);
+      a = __longlong_as_double((long long)(((ra >> 63) << 63) | (ea << 52) | ma));
+      b = __longlong_as_double((long long)(((rb >> 63) << 63) | (eb << 52) | mb));
+    }
+    const double q_ref = a / b;
+    const double q = div_rcp(a, b, rcp_refine(b));
+    const bool same = __double_as_longlong(q) == __double_as_longlong(q_ref) || (q != q && q_ref != q_ref);
+    if (!same) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -404,6 +436,48 @@ static int validate_cands(alore_ctx* ctx, const alore_candidates_t* c) {
 }
 
 extern "C" {
+
+int alore_debug_force_exact_division(alore_ctx* ctx, int on) {
+  if (!ctx) return ALORE_EINVAL;
+  ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
+  ALORE_CUDA(ctx, cudaDeviceSynchronize());
+  const int v = on ? 1 : 0;
+  ALORE_CUDA(ctx, cudaMemcpyToSymbol(g_force_exact_div, &v, sizeof(int)));
+  return ALORE_OK;
+}
+
+int alore_debug_phase_cycles(alore_ctx* ctx, unsigned long long* out32, int reset) {
+  if (!ctx || !out32) return ALORE_EINVAL;
+  ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
+  ALORE_CUDA(ctx, cudaDeviceSynchronize());
+#ifdef ALORE_PHASE_TIMING
+  ALORE_CUDA(ctx, cudaMemcpyFromSymbol(out32, g_phase_cycles, 32 * sizeof(unsigned long long)));
+  if (reset) { unsigned long long z[32] = {0}; ALORE_CUDA(ctx, cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z))); }
+  return ALORE_OK;
+#else
+  (void)reset;
+  std::memset(out32, 0, 32 * sizeof(unsigned long long));
+  return alore_fail(ctx, ALORE_EINVAL, "library built without -DALORE_PHASE_TIMING");
+#endif
+}
+
+int alore_selftest_division(alore_ctx* ctx, long long n_pairs, unsigned long long seed, long long* mismatches) {
+  if (!ctx || !mismatches || n_pairs <= 0) return ALORE_EINVAL;
+  ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* d = nullptr;
+  ALORE_CUDA(ctx, cudaMalloc(&d, sizeof(unsigned long long)));
+  cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream);
+  division_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n_pairs, seed, d);
+  ctx->launches++;
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return alore_fail(ctx, ALORE_ECUDA, "division self-test: %s", cudaGetErrorString(e));
+  *mismatches = (long long)h;
+  return ALORE_OK;
+}
 
 int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch** out) {
   if (!ctx || !out) return ALORE_EINVAL;

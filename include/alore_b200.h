@@ -276,6 +276,17 @@ int alore_final_collision_batch(alore_ctx* ctx, const alore_params_t* prm, int B
                                 const double* piece_T, const double* start_xy,
                                 int32_t* collided, double* min_dist);
 
+/* Self-test of the kernels' split IEEE division (csrc/traj_opt.cuh: rcp_refine + div_rcp, used on the dependent
+ * chains of the banded LU / triangular sweeps that replace minco.hpp:99-197) against the compiler's a / b on
+ * n_pairs generated operand pairs (all exponents, specials, solver-range magnitudes).  *mismatches = differing bits. */
+int alore_selftest_division(alore_ctx* ctx, long long n_pairs, unsigned long long seed, long long* mismatches);
+/* Test hook: on != 0 makes every banded-solver pass use the compiler's division (the path taken when a quotient
+ * leaves the split division's range); results must not change.  Process-wide for the context's device. */
+int alore_debug_force_exact_division(alore_ctx* ctx, int on);
+/* Developer hook: per-phase cycle totals of the optimizer kernels (only in builds with -DALORE_PHASE_TIMING;
+ * the product build returns ALORE_EINVAL).  out32[0..6] = cost_eval phases, [8..13] = penalty passes, [16] = L-BFGS update. */
+int alore_debug_phase_cycles(alore_ctx* ctx, unsigned long long* out32, int reset);
+
 /* Number of kernels this library has launched since alore_create (bench `gpu_launches`). */
 long long alore_launch_count(const alore_ctx* ctx);
 

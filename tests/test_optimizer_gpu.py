@@ -309,3 +309,30 @@ def test_missing_map_is_an_error(ctx):
     rc = c2.lib.alore_opt_batch(c2.h, C.byref(prm), C.byref(cs), C.byref(rs))
     assert rc == -3 and b"ESDF" in c2.lib.alore_last_error(c2.h)
     c2.close()
+
+
+def test_split_division_is_ieee_division(ctx):
+    """rcp_refine + div_rcp (csrc/traj_opt.cuh) replace `a / b` on the dependent chains of the banded LU and of the
+    triangular sweeps (minco.hpp:99-197).  They must return the bits of the compiler's IEEE division for every
+    operand pair: raw 64-bit patterns (all exponents, subnormals, Inf/NaN), solver-range magnitudes, near-equal
+    mantissas.  2^26 pairs per seed."""
+    import ctypes as C
+    for seed in (1, 0xA105E, 2 ** 40 + 7):
+        bad = C.c_longlong(-1)
+        ctx.check(ctx.lib.alore_selftest_division(ctx.h, 1 << 26, seed, C.byref(bad)))
+        assert bad.value == 0, f"seed {seed}: {bad.value} quotients differ from a / b"
+
+
+def test_exact_division_rerun_path_gives_same_bits(world, portable_trig, ctx):
+    """The banded-solver passes run with the speculative split division and are repeated with the compiler's
+    division when a quotient leaves the fast path's range.  Forcing that second path must not change a single bit."""
+    m, prm, pl, grid = world
+    legs = leg_batch(world, max_legs=24)
+    a = pl.minco_plan_batch(legs)
+    ctx.check(ctx.lib.alore_debug_force_exact_division(ctx.h, 1))
+    try:
+        b = pl.minco_plan_batch(legs)
+    finally:
+        ctx.check(ctx.lib.alore_debug_force_exact_division(ctx.h, 0))
+    assert np.array_equal(a.coeffs, b.coeffs) and np.array_equal(a.cost, b.cost) and np.array_equal(a.evals, b.evals)
+    assert np.array_equal(a.piece_T, b.piece_T) and np.array_equal(a.status, b.status)
