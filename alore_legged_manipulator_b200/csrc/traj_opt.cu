@@ -28,9 +28,8 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, doub
   w.pXY = s; s += 2 * (Nm + 1);
   w.sumT = s; s += Nm + 1 + 3;
   s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s) + 15) & ~uintptr_t(15));   // stg/stgb are accessed as double2
-  w.ring = s; s += 384;
-  w.stg = s; s += 304;
-  w.stgb = s;
+  w.ring = s; s += 256;
+  w.stg = s;
   w.Nm = Nm;
   w.cf = slab + L.cf; w.gC = slab + L.gC;
   w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp; w.d = slab + L.d;
