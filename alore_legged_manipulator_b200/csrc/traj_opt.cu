@@ -20,7 +20,7 @@ struct KParams {
 
 __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, double* hist, int N, int K) {
   w.lane = threadIdx.x & 31;
-  w.N = N; w.n = 3 * N - 1; w.n6 = 6 * N; w.K = K; w.S1 = 2 * K + 1;
+  w.N = N; w.n = 3 * N - 1; w.npad = (3 * N) & ~1; w.n6 = 6 * N; w.K = K; w.S1 = 2 * K + 1;
   const int Nm = L.Nmax;
   double* s = smem;
   w.T1 = s; s += Nm; w.T2 = s; s += Nm; w.T3 = s; s += Nm; w.T4 = s; s += Nm; w.T5 = s; s += Nm;
@@ -29,11 +29,13 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, doub
   w.sumT = s; s += Nm + 1 + 3;
   s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s) + 15) & ~uintptr_t(15));   // stg/stgb are accessed as double2
   w.ring = s; s += 256;
-  w.stg = s;
+  w.stg = s; s += 760;
+  w.d = s; s += L.npadmax;
+  w.hbuf = s;
   w.Nm = Nm;
   w.cf = slab + L.cf; w.gC = slab + L.gC;
-  w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp; w.d = slab + L.d;
-  w.lm_s = hist + L.lm_s; w.lm_y = hist + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys;
+  w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp;
+  w.lm_s = hist + L.lm_s; w.lm_y = hist + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys; w.lm_rys = slab + L.lm_rys;
   w.pf = slab + L.pf; w.Uf = slab + L.Ab; w.Lf = slab + L.Ab + (size_t)8 * 6 * Nm; w.zb = slab + L.zb; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
   w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
   w.terms = slab + L.terms; w.cg = slab + L.cg; w.fold = slab + L.fold;
