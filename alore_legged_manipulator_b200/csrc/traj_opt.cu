@@ -29,8 +29,8 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, doub
   w.sumT = s; s += Nm + 1 + 3;
   s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s) + 15) & ~uintptr_t(15));   // stg/stgb are accessed as double2
   w.ring = s; s += 256;
-  w.stg = s; s += 760;
   w.d = s; s += L.npadmax;
+  w.stg = s;
   w.hbuf = s;
   w.Nm = Nm;
   w.cf = slab + L.cf; w.gC = slab + L.gC;
