@@ -41,6 +41,11 @@ struct alore_ctx {
   size_t opt_scratch_bytes = 0;
   void* opt_hist = nullptr;      // L-BFGS history ring of every resident warp
   size_t opt_hist_bytes = 0;
+  // Scheduling memory across replan ticks: cost evaluations each candidate needed the last time a batch with the same
+  // structure (B, piece_off) was optimised.  The persistent kernel hands out the predicted-longest work first
+  // (results do not depend on the order; tests/test_optimizer_gpu.py::test_result_independent_of_batch_composition).
+  std::vector<int32_t> sched_piece_off;
+  std::vector<int32_t> sched_evals;
 };
 
 inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {

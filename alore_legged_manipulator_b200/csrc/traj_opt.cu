@@ -3,6 +3,7 @@
 // over the whole minco_plan (stage A L-BFGS, stage B augmented-Lagrangian loop of L-BFGS runs,
 // final collision check, collision replans) — no host round trip per iteration.
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "traj_opt.cuh"
@@ -358,6 +359,10 @@ int prepare_launch(alore_ctx* ctx, const alore_params_t* prm, int Nmax, int B, K
   int per_sm = 0;
   ALORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, L.smem));
   if (per_sm < 1) return alore_fail(ctx, ALORE_EINVAL, "kernel does not fit on an SM");
+  if (const char* e = getenv("ALORE_OPT_WARPS_PER_SM")) {   // tuning knob: resident candidate warps per SM (default: occupancy limit)
+    const int v = atoi(e);
+    if (v >= 1) per_sm = std::min(per_sm, v);
+  }
   L.slots = std::max(1, std::min(B, per_sm * ctx->sm_count));
   const size_t need = (size_t)L.slots * L.kp.L.total * sizeof(double) + 256;
   if (need > ctx->opt_scratch_bytes) {
@@ -426,7 +431,22 @@ struct alore_batch {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   double* d_best = nullptr;
   int* d_best_idx = nullptr;
+  std::vector<int32_t> piece_off;   // host copy (scheduling)
+  int* d_order = nullptr;
+  int runs = 0;
 };
+
+// Longest-processing-time-first order.  Work estimate of a candidate = pieces x cost evaluations of the previous
+// optimisation of the same batch structure when known (replanning re-optimises nearly the same candidates every
+// tick), else pieces alone.  Only the hand-out order of the work queue changes, never a result.
+static void lpt_order(const std::vector<int32_t>& po, const int32_t* evals, std::vector<int>& order) {
+  const int B = (int)po.size() - 1;
+  order.resize(B);
+  std::iota(order.begin(), order.end(), 0);
+  std::vector<long long> key(B);
+  for (int b = 0; b < B; b++) key[b] = (long long)(po[b + 1] - po[b]) * (evals ? std::max(1, evals[b]) : 1);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] > key[b]; });
+}
 
 static int validate_cands(alore_ctx* ctx, const alore_candidates_t* c) {
   if (!c || c->B <= 0 || !c->piece_off) return alore_fail(ctx, ALORE_EINVAL, "empty candidate batch");
@@ -491,11 +511,10 @@ int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch*
   const int B = c->B, tot = c->piece_off[B];
   bh->B = B; bh->tot = tot; bh->Nmax = max_pieces(c->piece_off, B);
   cudaStream_t st = ctx->stream;
-  std::vector<int> order(B);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    return (c->piece_off[a + 1] - c->piece_off[a]) > (c->piece_off[b + 1] - c->piece_off[b]);
-  });
+  bh->piece_off.assign(c->piece_off, c->piece_off + B + 1);
+  std::vector<int> order;
+  const bool known = (int)ctx->sched_evals.size() == B && ctx->sched_piece_off == bh->piece_off;
+  lpt_order(bh->piece_off, known ? ctx->sched_evals.data() : nullptr, order);
   int* d_po; int* d_order; double *d_ip, *d_T, *d_pos, *d_ss, *d_fs, *d_sx, *d_fx; unsigned char* d_cut;
 #define UP(dst, src, n)                                  \
   rc = dev_copy(ctx, &dst, src, (size_t)(n), st);        \
@@ -512,6 +531,7 @@ int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch*
   UP(d_fx, c->final_xytheta, 3 * (size_t)B)
   UP(d_cut, c->if_cut, B)
   bh->bt = BatchDev{B, d_po, d_ip, d_T, d_pos, d_ss, d_fs, d_sx, d_fx, d_cut, d_order};
+  bh->d_order = d_order;
   ResultDev& r = bh->res;
   const int* nul_i = nullptr; const double* nul_d = nullptr;
   UP(r.ok, nul_i, B) UP(r.status, nul_i, B) UP(r.replans, nul_i, B) UP(r.alm_iters, nul_i, B) UP(r.evals, nul_i, B)
@@ -533,6 +553,18 @@ int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, 
   Launch L;
   int rc = prepare_launch(ctx, prm, bh->Nmax, bh->B, opt_kernel, L, true);
   if (rc) return rc;
+  if (bh->runs > 0) {   // a resident batch that is optimised again: schedule by the work it needed last time
+    std::vector<int32_t> ev(bh->B);
+    ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), bh->res.evals, bh->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<int> order;
+    lpt_order(bh->piece_off, ev.data(), order);
+    ALORE_CUDA(ctx, cudaMemcpyAsync(bh->d_order, order.data(), bh->B * sizeof(int), cudaMemcpyHostToDevice, st));
+    ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->sched_piece_off = bh->piece_off;
+    ctx->sched_evals = ev;
+  }
+  bh->runs++;
   ALORE_CUDA(ctx, cudaMemsetAsync(L.counter, 0, sizeof(int), st));
   ALORE_CUDA(ctx, cudaEventRecord(bh->e0, st));
   set_l2_window(ctx, st, L.slabs, (size_t)L.slots * L.kp.L.total * sizeof(double));
@@ -555,7 +587,13 @@ int alore_batch_download(alore_ctx* ctx, alore_batch* bh, alore_results_t* out) 
   DN(out->evals, r.evals, B) DN(out->cost, r.cost, B) DN(out->inner_pts, r.inner_pts, 2 * (size_t)(tot - B))
   DN(out->tail_s, r.tail_s, B) DN(out->piece_T, r.piece_T, tot) DN(out->coeffs, r.coeffs, 12 * (size_t)tot)
 #undef DN
-  ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+  {
+    std::vector<int32_t> ev(B);
+    ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), r.evals, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->sched_piece_off = bh->piece_off;
+    ctx->sched_evals.swap(ev);
+  }
   cudaEventElapsedTime(&bh->kernel_ms, bh->e0, bh->e1);
   (void)cudaGetLastError();
   return ALORE_OK;

@@ -56,8 +56,12 @@ else:
         B = int(sys.argv[2]) if len(sys.argv) > 2 else bench.PER_GPU
         cands = bench.build_candidates(m.geom(), grid, m.distance_buffer_all_, 0, B)
         db = DeviceBatch(ctx, cands)
-        db.run(prm)
-        r = db.download()
+        reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+        for rep in range(reps):
+            db.run(prm)
+            r = db.download()
+            if reps > 1:
+                print("  run", rep, "kernel ms", db.kernel_ms())
         print("bench block done: kernel ms", db.kernel_ms(), "ok", int(r.ok.sum()), "evals", int(r.evals.sum()), "alg bytes", db.stats()[0])
     else:
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
