@@ -274,8 +274,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    first_tick_ms = None
     for _ in range(args.warmup):
         step_resident()
+        if first_tick_ms is None:
+            first_tick_ms = db.kernel_ms()                     # queue order from piece counts only (no previous tick)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -345,12 +348,16 @@ def main():
                                    f"8 GPUs = the 65k-candidate tick of configs[4])",
                        "candidates_total": total_B, "pieces_mean": float(tot[1]) / total_B, "sparseResolution": int(prm.sparseResolution),
                        "lbfgs_mem_size": int(prm.lbfgs.mem_size), "parallelism": f"candidate-sharded x{world}, ESDF replicated",
-                       "l2": "working set (per-warp L-BFGS history + scratch, > 1 GB) is larger than L2; no flush needed"},
+                       "l2": "working set (per-warp L-BFGS history + scratch, > 1 GB) is larger than L2; no flush needed",
+                       "schedule": "work queue handed out longest-predicted-first; prediction = pieces x cost evaluations of the previous "
+                                   "tick of the same batch structure (warm ticks, timed), pieces only on the first tick",
+                       "first_tick_kernel_ms": first_tick_ms},
             "roofline": {"bound": "hbm", "kernel": "opt_kernel", "achieved": float(tot[2]) / world / (k_avg / 1e3) / 1e9,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": float(tot[2]) / world / (k_avg / 1e3) / 1e9 / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": float(tot[2]) / world, "kernel_ms_per_launch": k_avg,
-                         "note": "FP64-latency/issue bound, not HBM bound: see DESIGN.md section 6"},
+                         "note": "not HBM bound: one warp per candidate walks dependent FP64 chains (banded LU, triangular sweeps, "
+                                 "two-loop recursion); DESIGN.md section 6 has the stall breakdown"},
             "esdf": esdf_info,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
