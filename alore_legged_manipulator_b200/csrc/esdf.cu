@@ -300,65 +300,105 @@ __device__ __forceinline__ double esdf_value(int best, bool neg, double gi) {
 
 // K2: column pass.  grid (ceil(NY/TY), ceil(NX/TX)), 256 threads = 128 columns x 2 row halves.
 // A probe of row x' contributes t^2 + g(x')^2 where g is the row distance of the SAME kind as the query cell
-// (0 for the other kind): g = max(sgn * R, 0) with sgn = +1 for free/unknown query cells, -1 for occupied ones.
+// (0 for the other kind).  Free/unknown query cells (the overwhelming majority) take the fast path: g = max(R, 0),
+// the tile is padded with +SENT outside the window so the loop carries no bounds checks, both sides of a step share
+// one square (min(max(a,0), max(b,0)) = max(min(a,b), 0)), t^2 is a running sum.  Occupied query cells (g = max(-R, 0))
+// take the general path.  sqrt of small squared distances comes from a shared-memory copy of the table.
+constexpr int SQRT_SMEM = 1024;
 template <bool SQ>
 __global__ void __launch_bounds__(256)
 esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
               double* __restrict__ dist, int gly, int min_x, int min_y, double gi, int ref_compat,
               int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
   __shared__ __align__(16) int16_t S[TX + 2 * HALO][TY];
+  __shared__ double s_sqrt[SQ ? 1 : SQRT_SMEM];
   const int X0 = blockIdx.y * TX, Y0 = blockIdx.x * TY;
   const int rlo = X0 - HALO;
+  const unsigned padw = (unsigned)SENT | ((unsigned)SENT << 16);
   for (int idx = threadIdx.x; idx < (TX + 2 * HALO) * (TY / 8); idx += 256) {
     const int row = idx / (TY / 8), v = idx % (TY / 8);
     const int xr = rlo + row, y = Y0 + v * 8;
-    uint4 val = make_uint4(0, 0, 0, 0);
+    uint4 val = make_uint4(padw, padw, padw, padw);
     if (xr >= 0 && xr < NX && y < pitch) val = *reinterpret_cast<const uint4*>(R + (size_t)xr * pitch + y);
     *reinterpret_cast<uint4*>(&S[row][v * 8]) = val;
   }
+  if (!SQ)
+    for (int k = threadIdx.x; k < SQRT_SMEM; k += 256) s_sqrt[k] = g_sqrt_tbl[k];
   __syncthreads();
   const int ty = threadIdx.x & (TY - 1), half = threadIdx.x / TY;
   const int y = Y0 + ty;
   if (y >= NY) return;
-  const bool interior = (rlo >= 0) && (X0 + TX + HALO <= NX);   // every probed row of this tile exists
+  if (!SQ && ref_compat && y == NY - 1) return;                  // the reference never writes the window's last column
   const int Xb = X0 + half * (TX / 2);
-  const int Xe = min(Xb + TX / 2, NX);
+  int Xe = min(Xb + TX / 2, NX);
+  if (!SQ && ref_compat) {
+    Xe = min(Xe, NX - 1);                                        // ... nor its last row
+    if (y == 0) Xe = min(Xe, 1);                                 // column 0, rows >= 1: esdf_quirk_col
+  }
   double* out = dist + (size_t)(Xb + min_x) * gly + y + min_y;
-  const bool skip_col = !SQ && ref_compat && (y == NY - 1);
+  const int16_t* colp = &S[Xb - rlo][ty];
+  // Register window of the column: g[i] = max(R, 0) of row X - W + i.  The first W steps of every search read it with
+  // static indices (no loads, no branches: extra candidates cannot lower an exact minimum); four query rows share one
+  // window position, then the window slides by four rows.  g == 0 marks an Occupied query cell (general path).
+  constexpr int W = 8, U = 4;
+  int g[2 * W + U];
+#pragma unroll
+  for (int i = 0; i < 2 * W + U; i++) g[i] = max((int)colp[(i - W) * TY], 0);
 #pragma unroll 1
-  for (int X = Xb; X < Xe; X++, out += gly) {
-    if (!SQ && ref_compat && (skip_col || X == NX - 1 || (y == 0 && X >= 1))) continue;
-    const int sx = X - rlo;
-    const int16_t* col = &S[sx][ty];
-    const int r0 = col[0];
-    const bool neg = r0 < 0;
-    const int sgn = neg ? -1 : 1;
-    int best = r0 * r0;
-    int t = 1;
-    if (interior) {
-      for (; t <= HALO; ++t) {
-        const int tt = t * t;
-        if (tt >= best) break;
-        const int a = max(sgn * (int)col[-t * TY], 0), b = max(sgn * (int)col[t * TY], 0);
-        best = min(best, min(a * a, b * b) + tt);
-      }
-    } else {
-      for (; t <= HALO; ++t) {
-        const int tt = t * t;
-        if (tt >= best) break;
-        if (X - t >= 0) { const int a = max(sgn * (int)col[-t * TY], 0); best = min(best, a * a + tt); }
-        if (X + t < NX) { const int b = max(sgn * (int)col[t * TY], 0); best = min(best, b * b + tt); }
+  for (int X = Xb; X < Xe; X += U, out += (size_t)U * gly, colp += U * TY) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (X + u < Xe) {
+        const int16_t* col = colp + u * TY;
+        const int gc = g[W + u];
+        const bool neg = gc == 0;
+        int best = gc * gc;
+        int t;
+        if (!neg) {
+#pragma unroll
+          for (int k = 1; k <= W; k++) {
+            const int m = min(g[W + u - k], g[W + u + k]);
+            best = min(best, m * m + k * k);
+          }
+          t = W + 1;
+          if (best > t * t) {
+            for (; t <= HALO; ++t) {
+              const int tt = t * t;
+              if (tt >= best) break;
+              const int m = max(min((int)col[-t * TY], (int)col[t * TY]), 0);
+              best = min(best, m * m + tt);
+            }
+          }
+        } else {
+          const int r0 = col[0];
+          best = r0 * r0;
+          for (t = 1; t <= HALO; ++t) {
+            const int tt = t * t;
+            if (tt >= best) break;
+            if (X + u - t >= 0) { const int a = max(-(int)col[-t * TY], 0); best = min(best, a * a + tt); }
+            if (X + u + t < NX) { const int b = max(-(int)col[t * TY], 0); best = min(best, b * b + tt); }
+          }
+        }
+        if (t > HALO && t * t < best && (X + u - t >= 0 || X + u + t < NX))
+          best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X + u, y, neg, best, t);
+        if (SQ) {
+          const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
+          pos_sq[(size_t)(X + u) * NY + y] = neg ? 0 : v;
+          neg_sq[(size_t)(X + u) * NY + y] = neg ? v : 0;
+        } else {
+          double root;
+          if (best < SQRT_SMEM) root = s_sqrt[best];
+          else if (best < SQRT_TBL) root = g_sqrt_tbl[best];
+          else root = (best >= SQ_SENT) ? sqrt(DBL_MAX) : sqrt((double)best);
+          const double dv = __dmul_rn(gi, root);                     // grid_interval_ * std::sqrt(val)
+          out[(size_t)u * gly] = neg ? __dadd_rn(0.0, __dadd_rn(-dv, gi)) : dv;      // all = pos(=0); all += (-neg + gi)
+        }
       }
     }
-    if (t > HALO && t * t < best && (X - t >= 0 || X + t < NX))
-      best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X, y, neg, best, t);
-    if (SQ) {
-      const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
-      pos_sq[(size_t)X * NY + y] = neg ? 0 : v;
-      neg_sq[(size_t)X * NY + y] = neg ? v : 0;
-    } else {
-      *out = esdf_value(best, neg, gi);
-    }
+#pragma unroll
+    for (int i = 0; i < 2 * W; i++) g[i] = g[i + U];
+#pragma unroll
+    for (int i = 0; i < U; i++) g[2 * W + i] = max((int)colp[(W + U + i) * TY], 0);
   }
 }
 
