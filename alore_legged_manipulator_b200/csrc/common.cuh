@@ -15,7 +15,9 @@ struct alore_ctx {
   int device = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                  // side stream: the ref_compat column runs beside K1b/K2
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   long long launches = 0;
 

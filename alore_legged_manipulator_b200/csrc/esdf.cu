@@ -238,18 +238,35 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
   }
 }
 
-// K1b: block minima for far-search pruning.  grid (ceil(NY/256), ceil(NX/BLK)).
-__global__ void esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch) {
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
-  if (y >= NY) return;
+// K1b: block minima for far-search pruning.  One thread = 8 columns x one 32-row block: 32 independent 16-byte loads,
+// minima of max(r,0) and max(-r,0) kept as packed int16 pairs.  grid (ceil(pitch/8/128), ceil(NX/BLK)), 128 threads.
+__device__ __forceinline__ unsigned max0_s2(unsigned v) { return __vmaxs2(v, 0u); }
+__global__ void __launch_bounds__(128)
+esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch) {
+  const int y0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (y0 >= pitch) return;
   const int x0 = blockIdx.y * BLK, x1 = min(x0 + BLK, NX);
-  int mp = SENT, mn = SENT;
+  const unsigned big = (unsigned)SENT | ((unsigned)SENT << 16);
+  unsigned mp[4] = {big, big, big, big}, mn[4] = {big, big, big, big};
+#pragma unroll 8
   for (int x = x0; x < x1; x++) {
-    const int r = R[(size_t)x * pitch + y];
-    mp = min(mp, r > 0 ? r : 0);
-    mn = min(mn, r < 0 ? -r : 0);
+    const uint4 v = *reinterpret_cast<const uint4*>(R + (size_t)x * pitch + y0);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      mp[q] = __vmins2(mp[q], max0_s2(w[q]));
+      mn[q] = __vmins2(mn[q], max0_s2(__vnegss2(w[q])));
+    }
   }
-  blk[(size_t)blockIdx.y * blk_pitch + y] = (uint32_t)mp | ((uint32_t)mn << 16);
+  uint32_t* dst = blk + (size_t)blockIdx.y * blk_pitch + y0;
+  uint32_t o[8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    o[2 * q] = (mp[q] & 0xffffu) | ((mn[q] & 0xffffu) << 16);
+    o[2 * q + 1] = (mp[q] >> 16) | (mn[q] & 0xffff0000u);
+  }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 // Search rows outside the shared-memory halo, block by block, pruned by the block minima.
@@ -490,7 +507,8 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
       esdf_row_pass16<8><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     else
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
-    esdf_block_min<<<dim3((NY + 255) / 256, nblk), 256, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
+    if (ref_compat && NX >= 3 && NY >= 2) ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // the aliased column forks here
+    esdf_block_min<<<dim3((pitch / 8 + 127) / 128, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
     ctx->launches += 2;
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
     return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
@@ -508,14 +526,19 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
       ctx->launches++;
     }
   } else {
+    // the aliased column only needs the row pass: it runs on the side stream beside K1b / K2 (disjoint output cells)
+    const bool side = quirk && NX >= 3;
+    if (side) {
+      ALORE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+      esdf_quirk_col<false><<<(NX + 127) / 128, 128, 0, ctx->stream2>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                                                       g.grid_interval, nullptr, nullptr);
+      ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+      ctx->launches++;
+    }
     esdf_col_pass<false><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
                                                g.grid_interval, ref_compat, nullptr, nullptr);
     ctx->launches++;
-    if (quirk && NX >= 3) {
-      esdf_quirk_col<false><<<(NX + 127) / 128, 128, 0, st>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
-                                                              g.grid_interval, nullptr, nullptr);
-      ctx->launches++;
-    }
+    if (side) ALORE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
   }
   ALORE_CUDA(ctx, cudaGetLastError());
   return ALORE_OK;
