@@ -139,6 +139,51 @@ esdf_row_pass(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int mi
   for (int y = (nv << 3) + threadIdx.x; y < NY; y += ROW_THREADS) dst[y] = s_d[y];
 }
 
+// Four block-wide exclusive scans in one pass (K1 fast path): max-scans from the left of a, b; min-scans from the
+// right of c, d.  Warp-level shuffles, then the 8 warp aggregates of all four quantities are scanned together by
+// warp 0 (lane = 8 * quantity + warp), two barriers in total.
+__device__ __forceinline__ void excl_scan4(int& a, int& b, int& c, int& d, int (*s_agg)[ROW_THREADS / 32], int identMax, int identMin) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int ia = a, ib = b, ic = c, id = d;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+    const int tc = __shfl_down_sync(0xffffffffu, ic, o), td = __shfl_down_sync(0xffffffffu, id, o);
+    if (lane >= o) { ia = max(ia, ta); ib = max(ib, tb); }
+    if (lane + o < 32) { ic = min(ic, tc); id = min(id, td); }
+  }
+  if (lane == 31) { s_agg[0][w] = ia; s_agg[1][w] = ib; }
+  if (lane == 0) { s_agg[2][w] = ic; s_agg[3][w] = id; }
+  // exclusive within the warp
+  int ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
+  int ec = __shfl_down_sync(0xffffffffu, ic, 1), ed = __shfl_down_sync(0xffffffffu, id, 1);
+  if (lane == 0) { ea = identMax; eb = identMax; }
+  if (lane == 31) { ec = identMin; ed = identMin; }
+  __syncthreads();
+  if (w == 0) {
+    const int q = lane >> 3, i = lane & 7;            // quantity, warp index
+    const bool isMax = q < 2;
+    int v = s_agg[q][i];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const int tu = __shfl_up_sync(0xffffffffu, inc, o), td2 = __shfl_down_sync(0xffffffffu, inc, o);
+      if (isMax) { if (i >= o) inc = max(inc, tu); }
+      else { if (i + o < 8) inc = min(inc, td2); }
+    }
+    const int xu = __shfl_up_sync(0xffffffffu, inc, 1), xd = __shfl_down_sync(0xffffffffu, inc, 1);   // both by all lanes
+    int ex = isMax ? xu : xd;
+    if (isMax && i == 0) ex = identMax;
+    if (!isMax && i == 7) ex = identMin;
+    s_agg[q][i] = ex;                                  // carry entering warp i
+  }
+  __syncthreads();
+  a = max(s_agg[0][w], ea);
+  b = max(s_agg[1][w], eb);
+  c = min(s_agg[2][w], ec);
+  d = min(s_agg[3][w], ed);
+}
+
 // K1 (fast path): rows that start on a 16-byte boundary.  Each thread owns GP consecutive groups of 16 cells;
 // a group is one 16-byte load turned into two 16-bit masks (Occupied / not Occupied), nearest seeds inside the
 // group come from clz/ffs on the masks, nearest seeds outside from block-wide scans of per-thread extremes.
@@ -151,7 +196,7 @@ template <int GP>
 __global__ void __launch_bounds__(ROW_THREADS)
 esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int min_x, int min_y, int NX, int NY,
                 int16_t* __restrict__ R, int pitch) {
-  __shared__ int s_warp[ROW_THREADS / 32];
+  __shared__ int s_agg[4][ROW_THREADS / 32];
   const int X = blockIdx.x;
   const size_t row0 = (size_t)(X + min_x) * gly + min_y;
   const int G = (NY + 15) >> 4;
@@ -181,10 +226,8 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
       if (fm[q]) { lastFree = g * 16 + 31 - __clz(fm[q]); if (firstFree == BIG) firstFree = g * 16 + __ffs(fm[q]) - 1; }
     }
   }
-  int lo = excl_scan_max(lastOcc, s_warp, -BIG);
-  int lf = excl_scan_max(lastFree, s_warp, -BIG);
-  const int no = excl_scan_min_rev(firstOcc, s_warp, BIG);
-  const int nf = excl_scan_min_rev(firstFree, s_warp, BIG);
+  int lo = lastOcc, lf = lastFree, no = firstOcc, nf = firstFree;
+  excl_scan4(lo, lf, no, nf, s_agg, -BIG, BIG);
   // nearest seed to the right of each owned group (suffix over the thread's own groups)
   int ro[GP], rf[GP];
   {
