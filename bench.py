@@ -261,6 +261,35 @@ def main():
     pl = MSPlanner(ctx, prm, m)
     db = DeviceBatch(ctx, cands)
 
+    # ---- BASELINE configs[2]: batched penalty + gradient of 4096 trajectories x 64 pieces on this 2048^2 ESDF ------
+    penalty_info = {}
+    if rank == 0:
+        Bp, Np = 4096, 64
+        po, coeffs, Tp, s_xy, f_xy = workloads.random_spline_batch(Bp, Np, gm, m.distance_buffer_all_, grid, seed=3)
+        dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
+        d_po, d_c, d_T, d_s, d_f = dev(po, np.int32), dev(coeffs, np.float64), dev(Tp, np.float64), dev(s_xy, np.float64), dev(f_xy, np.float64)
+        d_cost = torch.zeros(Bp, dtype=torch.float64, device="cuda")
+        d_gC = torch.zeros(Bp * Np * 12, dtype=torch.float64, device="cuda")
+        d_gT = torch.zeros(Bp * Np, dtype=torch.float64, device="cuda")
+        d_err = torch.zeros(Bp * 2, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        pv = lambda t: C.c_void_p(t.data_ptr())
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
+        for a, b in evs:
+            a.record(stream)
+            ctx.check(ctx.lib.alore_penalty_batch_dev(ctx.h, C.byref(prm), Bp, Bp * Np, pv(d_po), pv(d_c), pv(d_T), pv(d_s), pv(d_f),
+                                                      pv(d_cost), pv(d_gC), pv(d_gT), pv(d_err), sptr))
+            b.record(stream)
+        torch.cuda.synchronize()
+        p_ms = float(np.median(sorted(a.elapsed_time(b) for a, b in evs)[1:]))
+        pbytes = Bp * (8 * (26 * Np + 1) + 32 * int(prm.n_checkpoints) * Np * (int(prm.sparseResolution) + 1))
+        penalty_info = {"workload": "configs[2]: 4096 trajectories x 64 pieces, 16 half-steps/piece, 2048^2 ESDF, coefficient space",
+                        "kernel_ms": p_ms, "evals_per_s": Bp / p_ms * 1e3,
+                        "roofline": {"bound": "hbm", "achieved": pbytes / p_ms / 1e6, "peak": peak, "unit": "GB/s",
+                                     "frac": pbytes / p_ms / 1e6 / peak, "bytes_per_trajectory": pbytes // Bp,
+                                     "note": "FP64 dependent-chain bound (one warp per trajectory), not HBM bound"}}
+        del d_po, d_c, d_T, d_s, d_f, d_cost, d_gC, d_gT, d_err
+
     def step_resident():
         ctx.check(ctx.lib.alore_esdf_update_dev(ctx.h, C.byref(gm), None, 0, 0, geom.glx - 1, geom.gly - 1, None, 1, sptr))
         db.run(prm, sptr)
@@ -359,6 +388,7 @@ def main():
                          "note": "not HBM bound: one warp per candidate walks dependent FP64 chains (banded LU, triangular sweeps, "
                                  "two-loop recursion); DESIGN.md section 6 has the stall breakdown"},
             "esdf": esdf_info,
+            "penalty": penalty_info,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(tot[5]),

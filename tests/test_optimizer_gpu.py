@@ -336,3 +336,21 @@ def test_exact_division_rerun_path_gives_same_bits(world, portable_trig, ctx):
         ctx.check(ctx.lib.alore_debug_force_exact_division(ctx.h, 0))
     assert np.array_equal(a.coeffs, b.coeffs) and np.array_equal(a.cost, b.cost) and np.array_equal(a.evals, b.evals)
     assert np.array_equal(a.piece_T, b.piece_T) and np.array_equal(a.status, b.status)
+
+
+def test_rescheduled_second_tick_gives_same_bits(world, portable_trig, ctx):
+    """A resident batch that is optimised again is handed out longest-predicted-work-first (evaluation counts of the
+    previous tick).  Only the queue order changes: every result of the second tick must equal the first bit for bit,
+    and the one-shot API (which learns from the context's memory of the same batch structure) must agree as well."""
+    m, prm, pl, grid = world
+    cands = leg_batch(world, max_legs=64)
+    db = DeviceBatch(ctx, cands)
+    db.run(prm)
+    a = db.download()
+    db.run(prm)
+    b = db.download()
+    db.close()
+    c = pl.minco_plan_batch(cands)
+    for r in (b, c):
+        assert np.array_equal(a.coeffs, r.coeffs) and np.array_equal(a.cost, r.cost) and np.array_equal(a.evals, r.evals)
+        assert np.array_equal(a.piece_T, r.piece_T) and np.array_equal(a.status, r.status) and np.array_equal(a.ok, r.ok)
