@@ -46,6 +46,11 @@ struct alore_ctx {
   // Scheduling memory across replan ticks: cost evaluations each candidate needed the last time a batch with the same
   // structure (B, piece_off) was optimised.  The persistent kernel hands out the predicted-longest work first
   // (results do not depend on the order; tests/test_optimizer_gpu.py::test_result_independent_of_batch_composition).
+  // Device arena of the one-shot batch path (alore_opt_batch & co.): grown on demand, reused across calls, so that a
+  // replan tick does not pay ~50 cudaMalloc/cudaFree round trips.  One pooled batch at a time; others use cudaMalloc.
+  void* batch_pool = nullptr;
+  size_t batch_pool_bytes = 0;
+  bool batch_pool_busy = false;
   std::vector<int32_t> sched_piece_off;
   std::vector<int32_t> sched_evals;
 };

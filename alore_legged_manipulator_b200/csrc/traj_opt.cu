@@ -406,9 +406,17 @@ void set_l2_window(alore_ctx* ctx, cudaStream_t st, void* base, size_t bytes) {
 }
 
 template <typename T>
-int dev_copy(alore_ctx* ctx, T** dst, const T* src, size_t n, cudaStream_t st) {
+int dev_copy(alore_ctx* ctx, T** dst, const T* src, size_t n, cudaStream_t st, char** arena_cur = nullptr, char* arena_end = nullptr) {
   *dst = nullptr;
-  ALORE_CUDA(ctx, cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  if (arena_cur && *arena_cur) {
+    const size_t need = (bytes + 255) & ~size_t(255);
+    if (*arena_cur + need > arena_end) return alore_fail(ctx, ALORE_ECUDA, "batch arena exhausted");
+    *dst = reinterpret_cast<T*>(*arena_cur);
+    *arena_cur += need;
+  } else {
+    ALORE_CUDA(ctx, cudaMalloc(dst, bytes));
+  }
   if (n && src) ALORE_CUDA(ctx, cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
   return ALORE_OK;
 }
@@ -434,6 +442,9 @@ struct alore_batch {
   std::vector<int32_t> piece_off;   // host copy (scheduling)
   int* d_order = nullptr;
   int runs = 0;
+  bool pooled = false;              // device arrays carved from ctx->batch_pool
+  char* pool_cur = nullptr;
+  char* pool_end = nullptr;
 };
 
 // Longest-processing-time-first order.  Work estimate of a candidate = pieces x cost evaluations of the previous
@@ -500,7 +511,7 @@ int alore_selftest_division(alore_ctx* ctx, long long n_pairs, unsigned long lon
   return ALORE_OK;
 }
 
-int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch** out) {
+static int batch_upload_impl(alore_ctx* ctx, const alore_candidates_t* c, alore_batch** out, bool use_arena) {
   if (!ctx || !out) return ALORE_EINVAL;
   *out = nullptr;
   int rc = validate_cands(ctx, c);
@@ -516,10 +527,25 @@ int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch*
   const bool known = (int)ctx->sched_evals.size() == B && ctx->sched_piece_off == bh->piece_off;
   lpt_order(bh->piece_off, known ? ctx->sched_evals.data() : nullptr, order);
   int* d_po; int* d_order; double *d_ip, *d_T, *d_pos, *d_ss, *d_fs, *d_sx, *d_fx; unsigned char* d_cut;
+  if (use_arena && !ctx->batch_pool_busy) {   // one-shot calls carve every device array from the context's arena
+    const size_t need = 8 * (48 * (size_t)B + 40 * (size_t)tot) + 64 * 1024;
+    if (need > ctx->batch_pool_bytes) {
+      if (ctx->batch_pool) { cudaDeviceSynchronize(); cudaFree(ctx->batch_pool); }
+      ctx->batch_pool = nullptr; ctx->batch_pool_bytes = 0;
+      if (cudaMalloc(&ctx->batch_pool, need) == cudaSuccess) ctx->batch_pool_bytes = need;
+      else (void)cudaGetLastError();
+    }
+    if (ctx->batch_pool) {
+      ctx->batch_pool_busy = true;
+      bh->pooled = true;
+      bh->pool_cur = static_cast<char*>(ctx->batch_pool);
+      bh->pool_end = bh->pool_cur + ctx->batch_pool_bytes;
+    }
+  }
 #define UP(dst, src, n)                                  \
-  rc = dev_copy(ctx, &dst, src, (size_t)(n), st);        \
+  rc = dev_copy(ctx, &dst, src, (size_t)(n), st, bh->pooled ? &bh->pool_cur : nullptr, bh->pool_end); \
   if (rc) { alore_batch_free(bh); return rc; }           \
-  bh->allocs.push_back(dst);
+  if (!bh->pooled) bh->allocs.push_back(dst);
   UP(d_po, c->piece_off, B + 1)
   UP(d_order, order.data(), B)
   UP(d_ip, c->inner_pts, 2 * (size_t)(tot - B))
@@ -546,6 +572,8 @@ int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch*
   *out = bh;
   return ALORE_OK;
 }
+
+int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch** out) { return batch_upload_impl(ctx, c, out, false); }
 
 int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, void* cuda_stream) {
   if (!ctx || !prm || !bh) return ALORE_EINVAL;
@@ -651,6 +679,7 @@ void alore_batch_free(alore_batch* bh) {
   if (bh->ctx) cudaSetDevice(bh->ctx->device);
   cudaDeviceSynchronize();
   for (void* p : bh->allocs) cudaFree(p);
+  if (bh->pooled && bh->ctx) bh->ctx->batch_pool_busy = false;
   if (bh->e0) cudaEventDestroy(bh->e0);
   if (bh->e1) cudaEventDestroy(bh->e1);
   delete bh;
@@ -659,7 +688,7 @@ void alore_batch_free(alore_batch* bh) {
 int alore_opt_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_candidates_t* cands, alore_results_t* out) {
   if (!ctx || !prm || !out) return ALORE_EINVAL;
   alore_batch* bh = nullptr;
-  int rc = alore_batch_upload(ctx, cands, &bh);
+  int rc = batch_upload_impl(ctx, cands, &bh, true);
   if (rc) return rc;
   rc = alore_batch_run(ctx, prm, bh, nullptr);
   if (rc == ALORE_OK) rc = alore_batch_download(ctx, bh, out);
@@ -672,7 +701,7 @@ int alore_cost_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_cand
   if (!ctx || !prm || !x || !cost || !g) return ALORE_EINVAL;
   if (stage != 0 && stage != 1) return alore_fail(ctx, ALORE_EINVAL, "stage must be 0 (path) or 1");
   alore_batch* bh = nullptr;
-  int rc = alore_batch_upload(ctx, cands, &bh);
+  int rc = batch_upload_impl(ctx, cands, &bh, true);
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
   const int B = bh->B;
