@@ -372,6 +372,10 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
               int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
   __shared__ __align__(16) int16_t S[TX + 2 * HALO][TY];
   __shared__ double s_sqrt[SQ ? 1 : SQRT_SMEM];
+  constexpr int DEF_CAP = 3072;                                  // deferred cells held in the list (37 % of a tile)
+  __shared__ unsigned short s_list[DEF_CAP];
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
   const int X0 = blockIdx.y * TX, Y0 = blockIdx.x * TY;
   const int rlo = X0 - HALO;
   const unsigned padw = (unsigned)SENT | ((unsigned)SENT << 16);
@@ -387,8 +391,7 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   __syncthreads();
   const int ty = threadIdx.x & (TY - 1), half = threadIdx.x / TY;
   const int y = Y0 + ty;
-  if (y >= NY) return;
-  if (!SQ && ref_compat && y == NY - 1) return;                  // the reference never writes the window's last column
+  const bool skip_thread = !SQ && ref_compat && y == NY - 1;     // the reference never writes the window's last column
   const int Xb = X0 + half * (TX / 2);
   int Xe = min(Xb + TX / 2, NX);
   if (!SQ && ref_compat) {
@@ -399,66 +402,108 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   const int16_t* colp = &S[Xb - rlo][ty];
   // Register window of the column: g[i] = max(R, 0) of row X - W + i.  The first W steps of every search read it with
   // static indices (no loads, no branches: extra candidates cannot lower an exact minimum); four query rows share one
-  // window position, then the window slides by four rows.  g == 0 marks an Occupied query cell (general path).
+  // window position, then the window slides by four rows.  Cells that need more — Occupied query cells (g == 0) and
+  // free cells whose search is not finished after W steps — are DEFERRED: each thread keeps a 32-bit mask of its rows,
+  // the CTA compacts all deferred cells into a list and works it off with full lanes after the main sweep.
   constexpr int W = 8, U = 4;
-  int g[2 * W + U];
+  unsigned defer = 0u;
+  if (y < NY && !skip_thread) {
+    int g[2 * W + U];
 #pragma unroll
-  for (int i = 0; i < 2 * W + U; i++) g[i] = max((int)colp[(i - W) * TY], 0);
+    for (int i = 0; i < 2 * W + U; i++) g[i] = max((int)colp[(i - W) * TY], 0);
 #pragma unroll 1
-  for (int X = Xb; X < Xe; X += U, out += (size_t)U * gly, colp += U * TY) {
+    for (int X = Xb; X < Xe; X += U, out += (size_t)U * gly, colp += U * TY) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (X + u < Xe) {
-        const int16_t* col = colp + u * TY;
-        const int gc = g[W + u];
-        const bool neg = gc == 0;
-        int best = gc * gc;
-        int t;
-        if (!neg) {
+      for (int u = 0; u < U; u++) {
+        if (X + u < Xe) {
+          const int gc = g[W + u];
+          int best = gc * gc;
 #pragma unroll
           for (int k = 1; k <= W; k++) {
             const int m = min(g[W + u - k], g[W + u + k]);
             best = min(best, m * m + k * k);
           }
-          t = W + 1;
-          if (best > t * t) {
-            for (; t <= HALO; ++t) {
-              const int tt = t * t;
-              if (tt >= best) break;
-              const int m = max(min((int)col[-t * TY], (int)col[t * TY]), 0);
-              best = min(best, m * m + tt);
-            }
+          if (gc == 0 || best > (W + 1) * (W + 1)) {
+            defer |= 1u << (X + u - Xb);
+          } else if (SQ) {
+            pos_sq[(size_t)(X + u) * NY + y] = best;
+            neg_sq[(size_t)(X + u) * NY + y] = 0;
+          } else {
+            out[(size_t)u * gly] = __dmul_rn(gi, s_sqrt[best]);        // best <= 81: grid_interval_ * std::sqrt(val)
           }
-        } else {
-          const int r0 = col[0];
-          best = r0 * r0;
-          for (t = 1; t <= HALO; ++t) {
-            const int tt = t * t;
-            if (tt >= best) break;
-            if (X + u - t >= 0) { const int a = max(-(int)col[-t * TY], 0); best = min(best, a * a + tt); }
-            if (X + u + t < NX) { const int b = max(-(int)col[t * TY], 0); best = min(best, b * b + tt); }
-          }
-        }
-        if (t > HALO && t * t < best && (X + u - t >= 0 || X + u + t < NX))
-          best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X + u, y, neg, best, t);
-        if (SQ) {
-          const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
-          pos_sq[(size_t)(X + u) * NY + y] = neg ? 0 : v;
-          neg_sq[(size_t)(X + u) * NY + y] = neg ? v : 0;
-        } else {
-          double root;
-          if (best < SQRT_SMEM) root = s_sqrt[best];
-          else if (best < SQRT_TBL) root = g_sqrt_tbl[best];
-          else root = (best >= SQ_SENT) ? sqrt(DBL_MAX) : sqrt((double)best);
-          const double dv = __dmul_rn(gi, root);                     // grid_interval_ * std::sqrt(val)
-          out[(size_t)u * gly] = neg ? __dadd_rn(0.0, __dadd_rn(-dv, gi)) : dv;      // all = pos(=0); all += (-neg + gi)
         }
       }
+#pragma unroll
+      for (int i = 0; i < 2 * W; i++) g[i] = g[i + U];
+#pragma unroll
+      for (int i = 0; i < U; i++) g[2 * W + i] = max((int)colp[(W + U + i) * TY], 0);
     }
-#pragma unroll
-    for (int i = 0; i < 2 * W; i++) g[i] = g[i + U];
-#pragma unroll
-    for (int i = 0; i < U; i++) g[2 * W + i] = max((int)colp[(W + U + i) * TY], 0);
+  }
+  // ---- deferred cells: compact (thread, row) pairs into shared memory, then one cell per thread per round -----------
+  {
+    const int cntme = __popc(defer);
+    int base = DEF_CAP;
+    if (cntme) base = atomicAdd(&s_cnt, cntme);
+    if (base + cntme <= DEF_CAP) {
+      unsigned mk = defer;
+      while (mk) {
+        const int r = __ffs(mk) - 1;
+        mk &= mk - 1;
+        s_list[base++] = (unsigned short)((threadIdx.x << 5) | r);    // thread (8 bits) : row offset (5 bits)
+      }
+      defer = 0u;
+    } else {                                                          // list full: the thread keeps its cells
+      for (int i = base; i < min(base + cntme, DEF_CAP); i++) s_list[i] = 0xffffu;   // reserved but unused slots
+    }
+  }
+  __syncthreads();
+  const int ndef = min(s_cnt, DEF_CAP);
+  // list entries first (dense over the lanes), then whatever a thread had to keep (list overflow: dense maps)
+  for (int idx = threadIdx.x;; idx += 256) {
+    int th, r;
+    if (idx < ndef) {
+      const unsigned e = s_list[idx];
+      if ((e >> 5) >= 256) continue;                                  // slot reserved by a thread that did not fit
+      th = e >> 5; r = e & 31;
+    } else if (defer) {
+      th = threadIdx.x; r = __ffs(defer) - 1; defer &= defer - 1;
+    } else break;
+    const int cty = th & (TY - 1), chalf = th / TY;
+    const int X = X0 + chalf * (TX / 2) + r, yy = Y0 + cty;
+    const int16_t* col = &S[X - rlo][cty];
+    const int r0 = col[0];
+    const bool neg = r0 < 0;
+    int best = r0 * r0;
+    int t = 1;
+    if (!neg) {
+      for (; t <= HALO; ++t) {
+        const int tt = t * t;
+        if (tt >= best) break;
+        const int m = max(min((int)col[-t * TY], (int)col[t * TY]), 0);
+        best = min(best, m * m + tt);
+      }
+    } else {
+      for (; t <= HALO; ++t) {
+        const int tt = t * t;
+        if (tt >= best) break;
+        if (X - t >= 0) { const int a = max(-(int)col[-t * TY], 0); best = min(best, a * a + tt); }
+        if (X + t < NX) { const int b = max(-(int)col[t * TY], 0); best = min(best, b * b + tt); }
+      }
+    }
+    if (t > HALO && t * t < best && (X - t >= 0 || X + t < NX))
+      best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X, yy, neg, best, t);
+    if (SQ) {
+      const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
+      pos_sq[(size_t)X * NY + yy] = neg ? 0 : v;
+      neg_sq[(size_t)X * NY + yy] = neg ? v : 0;
+    } else {
+      double root;
+      if (best < SQRT_SMEM) root = s_sqrt[best];
+      else if (best < SQRT_TBL) root = g_sqrt_tbl[best];
+      else root = (best >= SQ_SENT) ? sqrt(DBL_MAX) : sqrt((double)best);
+      const double dv = __dmul_rn(gi, root);                     // grid_interval_ * std::sqrt(val)
+      dist[(size_t)(X + min_x) * gly + yy + min_y] = neg ? __dadd_rn(0.0, __dadd_rn(-dv, gi)) : dv;   // all = pos(=0); all += (-neg + gi)
+    }
   }
 }
 
