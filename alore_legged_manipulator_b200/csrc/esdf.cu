@@ -364,7 +364,7 @@ __device__ __forceinline__ double esdf_value(int best, bool neg, double gi) {
 // the tile is padded with +SENT outside the window so the loop carries no bounds checks, both sides of a step share
 // one square (min(max(a,0), max(b,0)) = max(min(a,b), 0)), t^2 is a running sum.  Occupied query cells (g = max(-R, 0))
 // take the general path.  sqrt of small squared distances comes from a shared-memory copy of the table.
-constexpr int SQRT_SMEM = 1024;
+constexpr int SQRT_SMEM = 128;    // the register-window path only looks up squared distances <= (W+1)^2 = 81
 template <bool SQ>
 __global__ void __launch_bounds__(256)
 esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
@@ -372,19 +372,29 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
               int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
   __shared__ __align__(16) int16_t S[TX + 2 * HALO][TY];
   __shared__ double s_sqrt[SQ ? 1 : SQRT_SMEM];
-  constexpr int DEF_CAP = 3072;                                  // deferred cells held in the list (37 % of a tile)
+  constexpr int DEF_CAP = 2048;                                  // deferred cells held in the list (25 % of a tile)
   __shared__ unsigned short s_list[DEF_CAP];
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   const int X0 = blockIdx.y * TX, Y0 = blockIdx.x * TY;
   const int rlo = X0 - HALO;
   const unsigned padw = (unsigned)SENT | ((unsigned)SENT << 16);
-  for (int idx = threadIdx.x; idx < (TX + 2 * HALO) * (TY / 8); idx += 256) {
-    const int row = idx / (TY / 8), v = idx % (TY / 8);
-    const int xr = rlo + row, y = Y0 + v * 8;
-    uint4 val = make_uint4(padw, padw, padw, padw);
-    if (xr >= 0 && xr < NX && y < pitch) val = *reinterpret_cast<const uint4*>(R + (size_t)xr * pitch + y);
-    *reinterpret_cast<uint4*>(&S[row][v * 8]) = val;
+  {
+    constexpr int NV = (TX + 2 * HALO) * (TY / 8) / 256;         // 16-byte vectors per thread: all loads first, then all stores
+    uint4 val[NV];
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      const int idx = threadIdx.x + q * 256;
+      const int row = idx / (TY / 8), v = idx % (TY / 8);
+      const int xr = rlo + row, y = Y0 + v * 8;
+      val[q] = make_uint4(padw, padw, padw, padw);
+      if (xr >= 0 && xr < NX && y < pitch) val[q] = *reinterpret_cast<const uint4*>(R + (size_t)xr * pitch + y);
+    }
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      const int idx = threadIdx.x + q * 256;
+      *reinterpret_cast<uint4*>(&S[idx / (TY / 8)][(idx % (TY / 8)) * 8]) = val[q];
+    }
   }
   if (!SQ)
     for (int k = threadIdx.x; k < SQRT_SMEM; k += 256) s_sqrt[k] = g_sqrt_tbl[k];
@@ -411,33 +421,38 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
     int g[2 * W + U];
 #pragma unroll
     for (int i = 0; i < 2 * W + U; i++) g[i] = max((int)colp[(i - W) * TY], 0);
+#define ALORE_K2_CELL(u)                                                                         \
+    {                                                                                            \
+      const int gc = g[W + (u)];                                                                 \
+      int best = gc * gc;                                                                        \
+      _Pragma("unroll") for (int k = 1; k <= W; k++) {                                           \
+        const int m = min(g[W + (u) - k], g[W + (u) + k]);                                       \
+        best = min(best, m * m + k * k);                                                         \
+      }                                                                                          \
+      if (gc == 0 || best > (W + 1) * (W + 1)) {                                                 \
+        defer |= 1u << (X + (u) - Xb);                                                           \
+      } else if (SQ) {                                                                           \
+        pos_sq[(size_t)(X + (u)) * NY + y] = best;                                               \
+        neg_sq[(size_t)(X + (u)) * NY + y] = 0;                                                  \
+      } else {                                                                                   \
+        out[(size_t)(u) * gly] = __dmul_rn(gi, s_sqrt[best]); /* best <= 81: gi * sqrt(val) */   \
+      }                                                                                          \
+    }
 #pragma unroll 1
     for (int X = Xb; X < Xe; X += U, out += (size_t)U * gly, colp += U * TY) {
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (X + u < Xe) {
-          const int gc = g[W + u];
-          int best = gc * gc;
-#pragma unroll
-          for (int k = 1; k <= W; k++) {
-            const int m = min(g[W + u - k], g[W + u + k]);
-            best = min(best, m * m + k * k);
-          }
-          if (gc == 0 || best > (W + 1) * (W + 1)) {
-            defer |= 1u << (X + u - Xb);
-          } else if (SQ) {
-            pos_sq[(size_t)(X + u) * NY + y] = best;
-            neg_sq[(size_t)(X + u) * NY + y] = 0;
-          } else {
-            out[(size_t)u * gly] = __dmul_rn(gi, s_sqrt[best]);        // best <= 81: grid_interval_ * std::sqrt(val)
-          }
-        }
+      if (X + U <= Xe) {                                   // whole group inside the tile: no per-cell guards
+        ALORE_K2_CELL(0) ALORE_K2_CELL(1) ALORE_K2_CELL(2) ALORE_K2_CELL(3)
+      } else {
+        if (X + 0 < Xe) ALORE_K2_CELL(0)
+        if (X + 1 < Xe) ALORE_K2_CELL(1)
+        if (X + 2 < Xe) ALORE_K2_CELL(2)
       }
 #pragma unroll
       for (int i = 0; i < 2 * W; i++) g[i] = g[i + U];
 #pragma unroll
       for (int i = 0; i < U; i++) g[2 * W + i] = max((int)colp[(W + U + i) * TY], 0);
     }
+#undef ALORE_K2_CELL
   }
   // ---- deferred cells: compact (thread, row) pairs into shared memory, then one cell per thread per round -----------
   {
