@@ -244,36 +244,39 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
   for (int q = 0; q < GP; q++) {
     const int g = g0 + q;
     if (g < G) {
-      // four running-distance recurrences over the 16 cells (nearest Occupied / nearest free, from the left / right)
+      // free/unknown cells: two running-distance recurrences (nearest Occupied from the left / from the right);
+      // Occupied cells (few): nearest free cell by bit scans over the group's masks, patched in afterwards
       const int y0 = g * 16;
-      int dl_o[16], dl_f[16];
+      int dl_o[16];
       {
-        int eo = y0 - 1 - lo, ef = y0 - 1 - lf;     // distance of cell -1 to the nearest seed on its left
+        int eo = y0 - 1 - lo;                       // distance of cell -1 to the nearest Occupied cell on its left
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           eo = ((om[q] >> i) & 1u) ? 0 : eo + 1;
-          ef = ((fm[q] >> i) & 1u) ? 0 : ef + 1;
           dl_o[i] = eo;
-          dl_f[i] = ef;
         }
       }
       unsigned outw[8];
       {
-        int eo = ro[q] - (y0 + 16), ef = rf[q] - (y0 + 16);   // distance of cell 16 to the nearest seed on its right
+        int eo = ro[q] - (y0 + 16);                 // distance of cell 16 to the nearest Occupied cell on its right
 #pragma unroll
         for (int i = 15; i >= 0; i--) {
-          const bool isocc = (om[q] >> i) & 1u;
-          eo = isocc ? 0 : eo + 1;
-          ef = ((fm[q] >> i) & 1u) ? 0 : ef + 1;
-          const int d = min(isocc ? min(dl_f[i], ef) : min(dl_o[i], eo), SENT);   // seeds of the OTHER kind
-          const int v = isocc ? -d : d;
-          if (i & 1) outw[i >> 1] = ((unsigned)v & 0xffffu) << 16;
-          else outw[i >> 1] |= (unsigned)v & 0xffffu;
+          eo = ((om[q] >> i) & 1u) ? 0 : eo + 1;
+          const int v = min(min(dl_o[i], eo), SENT);        // 0 at Occupied cells (patched below)
+          if (i & 1) outw[i >> 1] = (unsigned)v << 16;
+          else outw[i >> 1] |= (unsigned)v;
         }
       }
       int16_t* dst = R + (size_t)X * pitch + y0;
       reinterpret_cast<uint4*>(dst)[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
       reinterpret_cast<uint4*>(dst)[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+      for (unsigned m = om[q]; m; m &= m - 1) {
+        const int i = __ffs(m) - 1;
+        const unsigned fl = fm[q] & ((1u << i) - 1u), fr = fm[q] >> (i + 1);
+        const int dl = fl ? i - (31 - __clz(fl)) : (y0 + i) - lf;      // lf = -BIG when the row has no free cell to the left
+        const int dr = fr ? __ffs(fr) : rf[q] - (y0 + i);              // rf = BIG when none to the right
+        dst[i] = (int16_t)(-min(min(dl, dr), SENT));
+      }
       // carries for the next owned group
       if (om[q]) lo = y0 + 31 - __clz(om[q]);
       if (fm[q]) lf = y0 + 31 - __clz(fm[q]);
