@@ -284,35 +284,50 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
   }
 }
 
-// K1b: block minima for far-search pruning.  One thread = 8 columns x one 32-row block: 32 independent 16-byte loads,
-// minima of max(r,0) and max(-r,0) kept as packed int16 pairs.  grid (ceil(pitch/8/128), ceil(NX/BLK)), 128 threads.
+// K1b: block minima for far-search pruning.  Four lanes share one group of 8 columns, each taking 8 of the block's 32
+// rows (16-byte loads); minima of max(r,0) and max(-r,0) are kept as packed int16 pairs and combined by two xor
+// shuffles.  grid (ceil(pitch/8/32), ceil(NX/BLK)), 128 threads = 32 column groups x 4 row quarters.
 __device__ __forceinline__ unsigned max0_s2(unsigned v) { return __vmaxs2(v, 0u); }
 __global__ void __launch_bounds__(128)
 esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch) {
-  const int y0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (y0 >= pitch) return;
-  const int x0 = blockIdx.y * BLK, x1 = min(x0 + BLK, NX);
+  const int rq = threadIdx.x & 3;
+  const int y0 = (blockIdx.x * 32 + (threadIdx.x >> 2)) * 8;
+  const bool in = y0 < pitch;
+  const int x0 = blockIdx.y * BLK + rq * (BLK / 4), x1 = min(x0 + BLK / 4, NX);
   const unsigned big = (unsigned)SENT | ((unsigned)SENT << 16);
   unsigned mp[4] = {big, big, big, big}, mn[4] = {big, big, big, big};
-#pragma unroll 8
-  for (int x = x0; x < x1; x++) {
-    const uint4 v = *reinterpret_cast<const uint4*>(R + (size_t)x * pitch + y0);
-    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+  if (in) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      mp[q] = __vmins2(mp[q], max0_s2(w[q]));
-      mn[q] = __vmins2(mn[q], max0_s2(__vnegss2(w[q])));
+    for (int x = x0; x < x0 + BLK / 4; x++) {
+      if (x < x1) {
+        const uint4 v = *reinterpret_cast<const uint4*>(R + (size_t)x * pitch + y0);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          mp[q] = __vmins2(mp[q], max0_s2(w[q]));
+          mn[q] = __vmins2(mn[q], max0_s2(__vnegss2(w[q])));
+        }
+      }
     }
   }
-  uint32_t* dst = blk + (size_t)blockIdx.y * blk_pitch + y0;
-  uint32_t o[8];
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    o[2 * q] = (mp[q] & 0xffffu) | ((mn[q] & 0xffffu) << 16);
-    o[2 * q + 1] = (mp[q] >> 16) | (mn[q] & 0xffff0000u);
+  for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      mp[q] = __vmins2(mp[q], __shfl_xor_sync(0xffffffffu, mp[q], o));
+      mn[q] = __vmins2(mn[q], __shfl_xor_sync(0xffffffffu, mn[q], o));
+    }
+  if (in && rq == 0) {
+    uint32_t* dst = blk + (size_t)blockIdx.y * blk_pitch + y0;
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      o[2 * q] = (mp[q] & 0xffffu) | ((mn[q] & 0xffffu) << 16);
+      o[2 * q + 1] = (mp[q] >> 16) | (mn[q] & 0xffff0000u);
+    }
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
-  reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 // Search rows outside the shared-memory halo, block by block, pruned by the block minima.
@@ -614,7 +629,7 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
     else
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     if (ref_compat && NX >= 3 && NY >= 2) ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // the aliased column forks here
-    esdf_block_min<<<dim3((pitch / 8 + 127) / 128, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
+    esdf_block_min<<<dim3((pitch / 8 + 31) / 32, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
     ctx->launches += 2;
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
     return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
