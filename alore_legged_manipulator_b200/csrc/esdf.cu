@@ -433,7 +433,10 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   // window position, then the window slides by four rows.  Cells that need more — Occupied query cells (g == 0) and
   // free cells whose search is not finished after W steps — are DEFERRED: each thread keeps a 32-bit mask of its rows,
   // the CTA compacts all deferred cells into a list and works it off with full lanes after the main sweep.
-  constexpr int W = 8, U = 4;
+#ifndef ALORE_K2_W
+#define ALORE_K2_W 8
+#endif
+  constexpr int W = ALORE_K2_W, U = 4;
   unsigned defer = 0u;
   if (y < NY && !skip_thread) {
     int g[2 * W + U];

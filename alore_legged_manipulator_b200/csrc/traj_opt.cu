@@ -396,6 +396,7 @@ void set_l2_window(alore_ctx* ctx, cudaStream_t st, void* base, size_t bytes) {
     if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
   }
   if (max_persist <= 0 || max_window <= 0) return;
+  if (getenv("ALORE_NO_L2_WINDOW")) return;   // tuning knob
   cudaStreamAttrValue v{};
   v.accessPolicyWindow.base_ptr = base;
   v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
