@@ -354,3 +354,30 @@ def test_rescheduled_second_tick_gives_same_bits(world, portable_trig, ctx):
     for r in (b, c):
         assert np.array_equal(a.coeffs, r.coeffs) and np.array_equal(a.cost, r.cost) and np.array_equal(a.evals, r.evals)
         assert np.array_equal(a.piece_T, r.piece_T) and np.array_equal(a.status, r.status) and np.array_equal(a.ok, r.ok)
+
+
+def test_long_trajectories_and_fine_sampling(portable_trig):
+    """Long corridor legs (N ~ 50..130 pieces: the 8-elements-per-lane two-loop window, multi-chunk sweeps, the larger
+    shared-memory carve-up) and sparseResolution = 12 (cell-prefix chunking, larger term log) stay bit-identical."""
+    import alore_legged_manipulator_b200 as alore
+    ctx = alore.Context(0)
+    glx, gly = 3200, 160                                    # 160 m x 8 m at 0.05 m
+    grid = workloads.random_map(glx, gly, 11, p_occ=0.0, p_unknown=0.0, wall=True, boxes=30, box_cells=(4, 12))
+    grid.reshape(glx, gly)[:, 60:100] = capi.UNOCCUPIED     # a free lane down the middle
+    m = make_sdf(ctx, glx, gly, 0.05, grid)
+    m.updateESDF2d()
+    fts = []
+    for x1, th in ((-10.0, 0.0), (40.0, 0.3), (75.0, 0.0)):
+        fts.append(front_end.make_flat_traj([(-75.0, 0.0), (x1, 0.0)], (-75.0, 0.0, 0.0), (x1, 0.0, th)))
+    cands = front_end.pack_candidates(fts)
+    assert int(np.diff(cands.piece_off).max()) > 100
+    for K in (8, 12):
+        prm = capi.default_params()
+        prm.alm_max_outer = 6
+        prm.sparseResolution = K
+        pl = MSPlanner(ctx, prm, m)
+        res = pl.minco_plan_batch(cands)
+        ref = oracle_lib.opt_batch(prm, m.geom(), m.distance_buffer_all_, cands, 4)
+        assert check_results(res, ref, cands) == 0.0
+    m.close()
+    ctx.close()
