@@ -36,7 +36,7 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, doub
   w.Nm = Nm;
   w.cf = slab + L.cf; w.gC = slab + L.gC;
   w.x = slab + L.x; w.g = slab + L.g; w.xp = slab + L.xp; w.gp = slab + L.gp;
-  w.lm_s = hist + L.lm_s; w.lm_y = hist + L.lm_y; w.lm_alpha = slab + L.lm_alpha; w.lm_ys = slab + L.lm_ys; w.lm_rys = slab + L.lm_rys;
+  w.lm_s = hist + L.lm_s; w.lm_y = hist + L.lm_y;
   w.pf = slab + L.pf; w.Uf = slab + L.Ab; w.Lf = slab + L.Ab + (size_t)8 * 6 * Nm; w.zb = slab + L.zb; w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay;
   w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
   w.terms = slab + L.terms; w.cg = slab + L.cg; w.fold = slab + L.fold;
