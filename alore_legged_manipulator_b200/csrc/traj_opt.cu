@@ -216,7 +216,10 @@ cost_kernel(const __grid_constant__ KParams kp, BatchDev bt, int stage, const do
 }
 
 // attachPenaltyFunctional on given coefficients (BASELINE config 3).
-__global__ void __launch_bounds__(32)
+#ifndef ALORE_PEN_MINBLOCKS
+#define ALORE_PEN_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(32, ALORE_PEN_MINBLOCKS)
 penalty_kernel(const __grid_constant__ KParams kp, int B, const int* piece_off, const double* coeffs, const double* Ts,
                const double* start_xy, const double* final_xy, double* cost, double* gradC, double* gradT, double* err,
                double* slabs, int* counter) {
