@@ -462,6 +462,25 @@ static void lpt_order(const std::vector<int32_t>& po, const int32_t* evals, std:
   for (int b = 0; b < B; b++) key[b] = (long long)(po[b + 1] - po[b]) * (evals ? std::max(1, evals[b]) : 1);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] > key[b]; });
 }
+// Evaluation counts to predict from, for a batch with piece offsets `po`: the previous tick's counts where the previous
+// batch had the same number of candidates and (for at least 3 in 4 of them) the same piece count at the same index —
+// a replanning planner re-optimises mostly the same legs; candidates whose piece count changed get the mean count.
+// Returns false (piece counts only) when the previous batch does not look like this one.
+static bool predicted_evals(const alore_ctx* ctx, const std::vector<int32_t>& po, std::vector<int32_t>& pred) {
+  const int B = (int)po.size() - 1;
+  if ((int)ctx->sched_evals.size() != B || (int)ctx->sched_piece_off.size() != B + 1) return false;
+  long long same = 0, sum = 0;
+  for (int b = 0; b < B; b++) {
+    same += (po[b + 1] - po[b]) == (ctx->sched_piece_off[b + 1] - ctx->sched_piece_off[b]);
+    sum += ctx->sched_evals[b];
+  }
+  if (4 * same < 3LL * B) return false;
+  const int32_t mean = (int32_t)std::max<long long>(1, sum / B);
+  pred.resize(B);
+  for (int b = 0; b < B; b++)
+    pred[b] = (po[b + 1] - po[b]) == (ctx->sched_piece_off[b + 1] - ctx->sched_piece_off[b]) ? ctx->sched_evals[b] : mean;
+  return true;
+}
 
 static int validate_cands(alore_ctx* ctx, const alore_candidates_t* c) {
   if (!c || c->B <= 0 || !c->piece_off) return alore_fail(ctx, ALORE_EINVAL, "empty candidate batch");
@@ -528,8 +547,9 @@ static int batch_upload_impl(alore_ctx* ctx, const alore_candidates_t* c, alore_
   cudaStream_t st = ctx->stream;
   bh->piece_off.assign(c->piece_off, c->piece_off + B + 1);
   std::vector<int> order;
-  const bool known = (int)ctx->sched_evals.size() == B && ctx->sched_piece_off == bh->piece_off;
-  lpt_order(bh->piece_off, known ? ctx->sched_evals.data() : nullptr, order);
+  std::vector<int32_t> pred;
+  const bool known = predicted_evals(ctx, bh->piece_off, pred);
+  lpt_order(bh->piece_off, known ? pred.data() : nullptr, order);
   int* d_po; int* d_order; double *d_ip, *d_T, *d_pos, *d_ss, *d_fs, *d_sx, *d_fx; unsigned char* d_cut;
   if (use_arena && !ctx->batch_pool_busy) {   // one-shot calls carve every device array from the context's arena
     const size_t need = 8 * (48 * (size_t)B + 40 * (size_t)tot) + 64 * 1024;
