@@ -243,9 +243,32 @@ def main():
                                   "frac": 13 * cells / k_ms / 1e6 / peak, "bytes_per_cell": 13},
                      "e2e_ms": 1e3 * min(e2e_t[1:]), "e2e_mcells_per_s": cells / min(e2e_t[1:]) / 1e6,
                      "l2_flush_between_iterations": True}
-        del flush
         m2.close()
         del m2
+        # BASELINE configs[4] map: 8192 x 2048 corridor (40.96 m x 10.24 m at 0.005 m), full-window rebuild
+        nx4, ny4 = 8192, 2048
+        g4 = workloads.make_geom(nx4, ny4, 0.005)
+        m4 = alore.SDFmap(ctx, gridmap_interval=0.005, detection_range=1e6, global_x_lower=g4.x_lower,
+                          global_x_upper=g4.x_lower + (nx4 - 0.5) * 0.005, global_y_lower=g4.y_lower,
+                          global_y_upper=g4.y_lower + (ny4 - 0.5) * 0.005)
+        m4.gridmap_[:] = workloads.corridor_map(nx4, ny4, 5, width_cells=400, clutter=0.02)
+        m4.has_map_ = True
+        m4.updateESDF2d()
+        gg4 = m4.geom()
+        evs4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+        for a, b in evs4:
+            flush.fill_(1)
+            a.record(stream)
+            ctx.check(ctx.lib.alore_esdf_update_dev(ctx.h, C.byref(gg4), None, 0, 0, nx4 - 1, ny4 - 1, None, 1, sptr))
+            b.record(stream)
+        torch.cuda.synchronize()
+        k4 = float(np.median(sorted(a.elapsed_time(b) for a, b in evs4)))
+        esdf_info["long_route"] = {"workload": "configs[4] map: 8192x2048 corridor (2 m wide free lane, 2 % clutter, walls elsewhere), full-window rebuild",
+                                   "kernel_ms": k4, "mcells_per_s": nx4 * ny4 / k4 / 1e3,
+                                   "roofline_frac": 13 * nx4 * ny4 / k4 / 1e6 / peak}
+        del flush
+        m4.close()
+        del m4
 
     # ---- candidate workload ----------------------------------------------------------------------------------
     geom, grid = build_world()
