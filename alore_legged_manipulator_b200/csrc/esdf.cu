@@ -330,29 +330,71 @@ esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_
   }
 }
 
-// Search rows outside the shared-memory halo, block by block, pruned by the block minima.
+// K1c: second pruning level: minima over 32 consecutive blocks (1024 rows), stored behind the block rows of `blk`.
+constexpr int SBLK = 32;              // blocks per super-block
+__global__ void esdf_superblock_min(uint32_t* __restrict__ blk, int blk_pitch, int nblk) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= blk_pitch) return;
+  const int b0 = blockIdx.y * SBLK, b1 = min(b0 + SBLK, nblk);
+  unsigned mp = SENT, mn = SENT;
+  for (int b = b0; b < b1; b++) {
+    const uint32_t m = blk[(size_t)b * blk_pitch + y];
+    mp = min(mp, m & 0xffffu);
+    mn = min(mn, m >> 16);
+  }
+  blk[(size_t)(nblk + blockIdx.y) * blk_pitch + y] = mp | (mn << 16);
+}
+
+// Search rows t_start and further away from row X, super-block by super-block and block by block, pruned by the
+// minima of g over the (super-)block.  One load gives two bounds on the best candidate inside a block:
+//   lower  d_near^2 + min(g)^2  (skip the block if it cannot beat `best`),
+//   upper  d_far^2  + min(g)^2  (the row that attains min(g) is somewhere in the block: tightens `best` at once).
+// A first sweep over both directions only collects upper bounds, the second reads the rows of the blocks that are
+// still promising.  Exact: the bounds are conservative, every row that could matter is read.
 __device__ __noinline__ int esdf_far_search(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk,
                                             int blk_pitch, int NX, int X, int y, bool neg, int best, int t_start) {
+  const int nblk = (NX + BLK - 1) / BLK;
+  const uint32_t* __restrict__ blk2 = blk + (size_t)nblk * blk_pitch;
+  constexpr int SROWS = BLK * SBLK;
 #pragma unroll 1
-  for (int dir = -1; dir <= 1; dir += 2) {
-    int x = X + dir * t_start;
-    while (x >= 0 && x < NX) {
-      const int d = abs(x - X);
-      if (d * d >= best) break;
-      const int b = x / BLK;
-      const int bend = dir < 0 ? b * BLK : min(b * BLK + BLK - 1, NX - 1);
-      const uint32_t m = blk[(size_t)b * blk_pitch + y];
-      const int mg = neg ? (int)(m >> 16) : (int)(m & 0xffffu);
-      if (d * d + mg * mg < best) {
-        for (int xx = x;; xx += dir) {
-          const int r = R[(size_t)xx * pitch + y];
-          const int dd = xx - X;
-          const int c = ((r < 0) == neg) ? r * r : 0;
-          best = min(best, dd * dd + c);
-          if (xx == bend) break;
+  for (int pass = 0; pass < 2; pass++) {
+#pragma unroll 1
+    for (int dir = -1; dir <= 1; dir += 2) {
+      int x = X + dir * t_start;
+      while (x >= 0 && x < NX) {
+        int d = abs(x - X);
+        if (d * d >= best) break;
+        const int sb = x / SROWS;
+        const int send = dir < 0 ? sb * SROWS : min(sb * SROWS + SROWS - 1, NX - 1);
+        const uint32_t M = blk2[(size_t)sb * blk_pitch + y];
+        const int Mg = neg ? (int)(M >> 16) : (int)(M & 0xffffu);
+        if (d * d + Mg * Mg >= best) { x = send + dir; continue; }
+        while (dir < 0 ? x >= send : x <= send) {
+          d = abs(x - X);
+          if (d * d >= best) break;
+          const int b = x / BLK;
+          const int b0 = b * BLK, b1 = min(b0 + BLK - 1, NX - 1);
+          const int bend = dir < 0 ? b0 : b1;
+          const uint32_t m = blk[(size_t)b * blk_pitch + y];
+          const int mg = neg ? (int)(m >> 16) : (int)(m & 0xffffu);
+          if (pass == 0) {
+            if (mg < SENT) {
+              const int dfar = max(abs(b0 - X), abs(b1 - X));
+              best = min(best, dfar * dfar + mg * mg);
+            }
+          } else if (d * d + mg * mg < best) {
+            for (int xx = x;; xx += dir) {                      // rows in order of increasing distance from X
+              const int dd = xx - X;
+              if (dd * dd >= best) break;
+              const int r = R[(size_t)xx * pitch + y];
+              const int c = ((r < 0) == neg) ? r * r : 0;
+              best = min(best, dd * dd + c);
+              if (xx == bend) break;
+            }
+          }
+          x = bend + dir;
         }
       }
-      x = bend + dir;
     }
   }
   return best;
@@ -495,14 +537,21 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   __syncthreads();
   const int ndef = min(s_cnt, DEF_CAP);
   // list entries first (dense over the lanes), then whatever a thread had to keep (list overflow: dense maps)
+  // cells a thread kept for itself are consecutive rows of one column: the distance field is 1-Lipschitz along the
+  // column, so (sqrt(previous result) + 1)^2 is an upper bound for the next row of the same kind — it starts the
+  // search almost converged (large empty / solid regions).  Any valid upper bound keeps the search exact.
+  int prev_best = -1, prev_r = -2;
+  bool prev_neg = false;
   for (int idx = threadIdx.x;; idx += 256) {
     int th, r;
+    bool own = false;
     if (idx < ndef) {
       const unsigned e = s_list[idx];
       if ((e >> 5) >= 256) continue;                                  // slot reserved by a thread that did not fit
       th = e >> 5; r = e & 31;
     } else if (defer) {
       th = threadIdx.x; r = __ffs(defer) - 1; defer &= defer - 1;
+      own = true;
     } else break;
     const int cty = th & (TY - 1), chalf = th / TY;
     const int X = X0 + chalf * (TX / 2) + r, yy = Y0 + cty;
@@ -510,24 +559,33 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
     const int r0 = col[0];
     const bool neg = r0 < 0;
     int best = r0 * r0;
+    if (own && prev_best >= 0 && r == prev_r + 1 && neg == prev_neg && prev_best < SQ_SENT) {
+      const int sq = (int)sqrt((double)prev_best) + 1;        // >= ceil(sqrt(prev_best))
+      best = min(best, prev_best + 2 * sq + 1);
+    }
     int t = 1;
+    // Row by row inside the halo while the running bound is small; a bound that is still far beyond the halo after
+    // TSW rows (cells deep inside large solid / empty regions) switches to the block-pruned search right away
+    // instead of walking all 32 halo rows first.
+    constexpr int TSW = 6, FAR2 = (HALO + 1) * (HALO + 1);
     if (!neg) {
       for (; t <= HALO; ++t) {
         const int tt = t * t;
-        if (tt >= best) break;
+        if (tt >= best || (t > TSW && best > FAR2)) break;
         const int m = max(min((int)col[-t * TY], (int)col[t * TY]), 0);
         best = min(best, m * m + tt);
       }
     } else {
       for (; t <= HALO; ++t) {
         const int tt = t * t;
-        if (tt >= best) break;
+        if (tt >= best || (t > TSW && best > FAR2)) break;
         if (X - t >= 0) { const int a = max(-(int)col[-t * TY], 0); best = min(best, a * a + tt); }
         if (X + t < NX) { const int b = max(-(int)col[t * TY], 0); best = min(best, b * b + tt); }
       }
     }
-    if (t > HALO && t * t < best && (X - t >= 0 || X + t < NX))
+    if (t * t < best && (X - t >= 0 || X + t < NX))      // rows left to look at: beyond the halo, or switched early
       best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X, yy, neg, best, t);
+    if (own) { prev_best = best; prev_r = r; prev_neg = neg; }
     if (SQ) {
       const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
       pos_sq[(size_t)X * NY + yy] = neg ? 0 : v;
@@ -598,7 +656,7 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
   const int pitch = ((NY + TY - 1) / TY) * TY;
   const int nblk = (NX + BLK - 1) / BLK;
   if (!sq) {
-    const size_t need_row = (size_t)NX * pitch, need_blk = (size_t)nblk * pitch;
+    const size_t need_row = (size_t)NX * pitch, need_blk = (size_t)(nblk + (nblk + SBLK - 1) / SBLK) * pitch;
     if (need_row > ctx->row_cap) {
       if (ctx->d_row) cudaFree(ctx->d_row);
       ctx->d_row = nullptr;
@@ -633,6 +691,8 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     if (ref_compat && NX >= 3 && NY >= 2) ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // the aliased column forks here
     esdf_block_min<<<dim3((pitch / 8 + 31) / 32, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
+    esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
+    ctx->launches++;
     ctx->launches += 2;
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
     return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
