@@ -332,6 +332,7 @@ esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_
 
 // K1c: second pruning level: minima over 32 consecutive blocks (1024 rows), stored behind the block rows of `blk`.
 constexpr int SBLK = 32;              // blocks per super-block
+constexpr int SB_MIN_BLOCKS = 128;    // windows of more than 4096 rows get the second level (a launch is not free)
 __global__ void esdf_superblock_min(uint32_t* __restrict__ blk, int blk_pitch, int nblk) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
   if (y >= blk_pitch) return;
@@ -354,6 +355,7 @@ __global__ void esdf_superblock_min(uint32_t* __restrict__ blk, int blk_pitch, i
 __device__ __noinline__ int esdf_far_search(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk,
                                             int blk_pitch, int NX, int X, int y, bool neg, int best, int t_start) {
   const int nblk = (NX + BLK - 1) / BLK;
+  const bool two_level = nblk > SB_MIN_BLOCKS;        // the super-block row exists only for long windows (K1c)
   const uint32_t* __restrict__ blk2 = blk + (size_t)nblk * blk_pitch;
   constexpr int SROWS = BLK * SBLK;
 #pragma unroll 1
@@ -366,9 +368,11 @@ __device__ __noinline__ int esdf_far_search(const int16_t* __restrict__ R, int p
         if (d * d >= best) break;
         const int sb = x / SROWS;
         const int send = dir < 0 ? sb * SROWS : min(sb * SROWS + SROWS - 1, NX - 1);
-        const uint32_t M = blk2[(size_t)sb * blk_pitch + y];
-        const int Mg = neg ? (int)(M >> 16) : (int)(M & 0xffffu);
-        if (d * d + Mg * Mg >= best) { x = send + dir; continue; }
+        if (two_level) {
+          const uint32_t M = blk2[(size_t)sb * blk_pitch + y];
+          const int Mg = neg ? (int)(M >> 16) : (int)(M & 0xffffu);
+          if (d * d + Mg * Mg >= best) { x = send + dir; continue; }
+        }
         while (dir < 0 ? x >= send : x <= send) {
           d = abs(x - X);
           if (d * d >= best) break;
@@ -691,8 +695,10 @@ int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     if (ref_compat && NX >= 3 && NY >= 2) ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // the aliased column forks here
     esdf_block_min<<<dim3((pitch / 8 + 31) / 32, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
-    esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
-    ctx->launches++;
+    if (nblk > SB_MIN_BLOCKS) {
+      esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
+      ctx->launches++;
+    }
     ctx->launches += 2;
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
     return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
