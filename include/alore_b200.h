@@ -248,11 +248,17 @@ int alore_cost_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_cand
                      const double* safe_dis, double* cost, double* g, double* xy_err);
 
 /* ---- full optimisation, batched: B x MSPlanner::minco_plan (optimizer.cpp:169-220) ---- */
-/* HOST pointers in cands/out.  B = 1 reproduces one minco_plan call. */
+/* HOST pointers in cands/out.  B = 1 reproduces one minco_plan call.  Blocking.  The device copies of the batch are
+ * carved from an arena the context keeps (no cudaMalloc/cudaFree per call), and the hand-out order of the candidates
+ * to the resident warps uses the evaluation counts of the previous call with a similar batch (same B, same piece
+ * count at the same index for >= 3/4 of the candidates): longest predicted work first.  Neither affects a result:
+ * every candidate is optimised independently and deterministically. */
 int alore_opt_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_candidates_t* cands,
                     alore_results_t* out);
 
-/* Upload once / optimise many: device-resident candidate batch (HBM-resident timing path). */
+/* Upload once / optimise many: device-resident candidate batch (HBM-resident timing path).  alore_batch_run is
+ * asynchronous on cuda_stream (NULL = the context's stream) except that a handle which is run AGAIN first reads
+ * back its previous evaluation counts (one small blocking copy on that stream) to re-order its work queue. */
 typedef struct alore_batch alore_batch;
 int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* cands, alore_batch** out);
 int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* batch, void* cuda_stream);
