@@ -9,15 +9,22 @@
 //                         Occupied cell     : -d to the nearest non-Occupied cell in its row (-32767: none)
 //                       One value encodes both of the reference's first passes because a cell is a seed of
 //                       exactly one of the two transforms (sdf_map.cpp:635 vs :655-657).
-//   K1b esdf_block_min  per (32-row block, column) minima of g+ and g- (pruning bounds for K2's far search)
-//   K2  esdf_col_pass   exact column transform  val(X) = min_x' (X-x')^2 + g(x')^2  by an expanding search
-//                       with the t*t >= best cut-off, rows staged in shared memory (tile + halo), then
-//                       dist = gi*sqrt(val) and the reference's pos/neg combine (sdf_map.cpp:671-679).
+//   K1b esdf_block_min  per (32-row block, column) minima of g+ and g- (pruning bounds for K2's far search);
+//   K1c esdf_superblock_min  the same over 1024 rows, only for windows longer than 4096 rows
+//   K2  esdf_col_pass   exact column transform  val(X) = min_x' (X-x')^2 + g(x')^2 :
+//                         main sweep  — per thread a register window of its column (tile + halo staged in shared
+//                                       memory): the first 8 search steps without loads or branches;
+//                         deferred    — cells that need more (Occupied cells, longer searches) are compacted in
+//                                       shared memory and finished with full lanes: expanding search with the
+//                                       t*t >= best cut-off, then a block-/super-block-pruned search with lower and
+//                                       upper bounds from the minima, a Lipschitz bound chained along a column;
+//                       then dist = gi*sqrt(val) and the reference's pos/neg combine (sdf_map.cpp:671-679).
 //   K2q esdf_quirk_col  ref_compat: window-local column 0 is recomputed from the aliased input the
-//                       reference actually reads.
+//                       reference actually reads; side stream.
 // All arithmetic on squared distances is int32 (exact); the only FP ops are sqrt.rn.f64, mul.rn.f64 and
-// add.rn.f64, IEEE-identical to the CPU.  HBM-bound by design: 1 B/cell in, 2+2 B/cell intermediate
-// (L2-resident at 4096^2), 8 B/cell out.
+// add.rn.f64, IEEE-identical to the CPU.  Traffic: 1 B/cell in, 2+2 B/cell intermediate (L2-resident at 4096^2),
+// 8 B/cell out; on cluttered maps the kernels are ALU-issue bound at 0.40 of the 13 B/cell HBM roofline, on maps
+// with large empty / solid regions the O(distance) search dominates.
 #include <cfloat>
 
 #include "common.cuh"
