@@ -34,7 +34,10 @@ namespace {
 constexpr int SENT = 32767;
 constexpr int SQ_SENT = SENT * SENT;  // 1073676289: anything >= this is "no seed" (DBL_MAX in the reference)
 constexpr int BLK = 32;               // rows per pruning block
-constexpr int TX = 64, TY = 128, HALO = 32;
+#ifndef ALORE_K2_HALO
+#define ALORE_K2_HALO 32
+#endif
+constexpr int TX = 64, TY = 128, HALO = ALORE_K2_HALO;   // halo rows >= W + U - 1 of the register window
 constexpr int ROW_THREADS = 256;
 
 __device__ __forceinline__ int excl_scan_max(int v, int* s_warp, int ident) {
