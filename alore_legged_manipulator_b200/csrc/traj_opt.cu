@@ -30,6 +30,7 @@ __device__ void carve(Warp& w, const Layout& L, double* smem, double* slab, doub
   w.sumT = s; s += Nm + 1 + 3;
   s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s) + 15) & ~uintptr_t(15));   // stg/stgb are accessed as double2
   w.ring = s; s += 256;
+  w.mbar = s; s += 6;                 // 4 mbarriers + phase word (TMA history variant), keeps 16-byte alignment
   w.d = s; s += L.npadmax;
   w.stg = s;
   w.hbuf = s;
@@ -170,6 +171,13 @@ opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, doubl
   double* slab = slabs + (size_t)blockIdx.x * kp.L.total;
   double* hist = hists + (size_t)blockIdx.x * kp.L.hist_total;
   const int lane = threadIdx.x & 31;
+#ifdef ALORE_TMA_HISTORY
+  {
+    Warp w0;
+    carve(w0, kp.L, smem, slab, hist, 1, kp.P.sparseResolution);
+    lbfgs_tma_init(w0.mbar);
+  }
+#endif
   for (;;) {
     const int job = next_job(counter, lane);
     if (job >= bt.B) break;
