@@ -255,7 +255,7 @@ EXPORTED_SYMBOLS = [
     "alore_esdf_last_kernel_ms", "alore_penalty_batch", "alore_penalty_batch_dev", "alore_cost_batch",
     "alore_opt_batch", "alore_batch_upload", "alore_batch_run", "alore_batch_download",
     "alore_batch_device_results", "alore_batch_argmin", "alore_batch_last_kernel_ms", "alore_batch_stats", "alore_batch_free",
-    "alore_final_collision_batch", "alore_selftest_division", "alore_debug_force_exact_division", "alore_debug_phase_cycles", "alore_launch_count",
+    "alore_final_collision_batch", "alore_selftest_division", "alore_debug_force_exact_division", "alore_debug_phase_cycles", "alore_debug_wave_counters", "alore_launch_count",
 ]
 
 

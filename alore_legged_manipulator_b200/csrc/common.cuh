@@ -53,6 +53,9 @@ struct alore_ctx {
   bool batch_pool_busy = false;
   std::vector<int32_t> sched_piece_off;
   std::vector<int32_t> sched_evals;
+  // wavefront optimizer: pinned slots + events through which the host polls the survivor count (never per round)
+  int* h_poll = nullptr;
+  cudaEvent_t poll_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {

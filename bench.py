@@ -300,7 +300,7 @@ def main():
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
         for a, b in evs:
             a.record(stream)
-            ctx.check(ctx.lib.alore_penalty_batch_dev(ctx.h, C.byref(prm), Bp, Bp * Np, pv(d_po), pv(d_c), pv(d_T), pv(d_s), pv(d_f),
+            ctx.check(ctx.lib.alore_penalty_batch_dev(ctx.h, C.byref(prm), Bp, Np, pv(d_po), pv(d_c), pv(d_T), pv(d_s), pv(d_f),
                                                       pv(d_cost), pv(d_gC), pv(d_gT), pv(d_err), sptr))
             b.record(stream)
         torch.cuda.synchronize()

@@ -228,8 +228,11 @@ int alore_penalty_batch(alore_ctx* ctx, const alore_params_t* prm, int B, const 
                         const double* start_xy, const double* final_xy,
                         double* cost, double* gradC, double* gradT, double* xy_err);
 
-/* Same with DEVICE pointers, asynchronous on cuda_stream (kernel timing / HBM-resident path). */
-int alore_penalty_batch_dev(alore_ctx* ctx, const alore_params_t* prm, int B, int total_pieces,
+/* Same with DEVICE pointers, asynchronous on cuda_stream (kernel timing / HBM-resident path).
+ * max_pieces = an upper bound on N_b = piece_off[b+1]-piece_off[b] over the batch (the offsets live on the device, so
+ * the caller states it; shared memory and scratch are sized from it).  A trajectory with more pieces than declared is
+ * NOT evaluated: its cost comes back NaN and nothing is written out of bounds. */
+int alore_penalty_batch_dev(alore_ctx* ctx, const alore_params_t* prm, int B, int max_pieces,
                             const int32_t* d_piece_off, const double* d_coeffs, const double* d_piece_T,
                             const double* d_start_xy, const double* d_final_xy,
                             double* d_cost, double* d_gradC, double* d_gradT, double* d_xy_err,
@@ -292,6 +295,9 @@ int alore_debug_force_exact_division(alore_ctx* ctx, int on);
 /* Developer hook: per-phase cycle totals of the optimizer kernels (only in builds with -DALORE_PHASE_TIMING;
  * the product build returns ALORE_EINVAL).  out32[0..6] = cost_eval phases, [8..13] = penalty passes, [16] = L-BFGS update. */
 int alore_debug_phase_cycles(alore_ctx* ctx, unsigned long long* out32, int reset);
+
+/* Developer hook: cycle / event counters of the wavefront optimizer's kernels (csrc/wave_opt.cuh g_wave_dbg): 16 values. */
+int alore_debug_wave_counters(alore_ctx* ctx, unsigned long long* out16, int reset);
 
 /* Number of kernels this library has launched since alore_create (bench `gpu_launches`). */
 long long alore_launch_count(const alore_ctx* ctx);
