@@ -502,7 +502,7 @@ int wave_prepare(alore_ctx* ctx, const alore_params_t* prm, int B, int tot, int 
   L.kp.Nmax = Nmax;
   L.kp.npadmax = (3 * Nmax) & ~1;
   L.kp.mcap = std::max(1, mcap);
-  L.smem_solve = (size_t)wave::SOLVE_WARPS * 4 * wave::GS * sizeof(double);
+  L.smem_solve = (size_t)wave::SOLVE_WARPS * 4 * wave::GS * sizeof(double) + wave::GTAB * (sizeof(double) + sizeof(int));
   L.smem_pen = wave::pen_smem_doubles(Nmax) * sizeof(double);
   L.smem_step = wave::step_smem_doubles(Nmax) * sizeof(double);
   if (L.smem_pen > 200 * 1024 || L.smem_step > 200 * 1024)

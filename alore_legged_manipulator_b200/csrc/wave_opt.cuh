@@ -88,10 +88,16 @@ struct WParams {
 
 // =====================================================================================================
 // 8-lane groups: banded LU and triangular sweeps (minco.hpp:99-197), 4 candidates per warp
+//
+// These kernels are chains of dependent issues (a lone warp issues one instruction every ~4.6 cycles), so their time
+// is their instruction count: the pivot loop is unrolled by 7 with the entry of column j in register j % 7 (nothing
+// ever shifts), the sweeps are unrolled by 2 with ping-pong operand sets (loads of the next row are issued before the
+// quotient of the current one), and the per-lane generator constants live in a shared table.
 // =====================================================================================================
-constexpr int GS = 456;          // doubles of shared memory per group: LU row ring (256) / sweep staging (2 x 220), T-power table (8)
-constexpr int CH = 16;           // rows per sweep chunk
-constexpr int SB = 220;          // doubles per staging buffer: 22 records of 8 + 22 rhs pairs
+constexpr int CH = 12;           // rows per sweep chunk
+constexpr int SB = 180;          // doubles per staging buffer: 18 records of 8 + 18 rhs pairs
+constexpr int GS = 368;          // doubles of shared memory per group: LU row ring (256) + T-power table (8) / sweep staging (2 x 180)
+constexpr int GTAB = 6 * 16;     // generator table entries (row type q = 0..5, ring column 0..15), once per CTA
 
 __device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(FULL, v, src, 8); }
 
@@ -127,152 +133,174 @@ __device__ __noinline__ void gen_row_generic(double* ring, int r, int n6, const 
   }
 }
 
+// The CTA-wide generator table: coefficient and T-power index of ring column `col` of knot row type q.
+__device__ __forceinline__ void gen_table_init(double* gcoef, int* gidx) {
+  for (int e = threadIdx.x; e < GTAB; e += blockDim.x) {
+    const int q = e >> 4, col = e & 15;
+    const int pw = col < 13 ? g_row_pow[q][col] : -1;
+    gcoef[e] = pw >= 0 ? g_row_coef[q][col] : 0.0;             // structural zero: 0.0 * 1.0
+    gidx[e] = pw > 0 ? pw : 0;                                 // index into tp[]: 0 -> 1.0
+  }
+}
+
+struct GenState {          // row generator of one group (warp-uniform gen_next; Tn / rn fetched one block ahead)
+  int gen_next;
+  double Tn, rn;
+};
+// Rows gen_next .. gen_next + 5 -> ring.  Knot blocks from the table (12 values per lane), blocks past the matrix edge
+// as zeros, the blocks holding head / tail rows through the generic generator.
+__device__ __noinline__ void gen_block(double* ring, double* tp, const double* gcoef, const int* gidx, GenState& gsn, int n6,
+                                       const double* xg, const double* T1g, const double* hs, const double* ts, double tail_s) {
+  const int l8 = lane_id() & 7;
+  const int gen_next = gsn.gen_next;
+  const bool knot = gen_next < n6 - 3;
+  const bool beyond = gen_next >= n6;                        // the whole block lies past the matrix edge: zero rows
+  const bool rhs_lane = l8 == 5 || l8 == 6;                  // ring columns 13 / 14 of row type 2: rhs = inner point p
+  if (knot) {
+    const double Tn = gsn.Tn, t2 = Tn * Tn;
+    const double pv = l8 == 1 ? Tn : l8 == 2 ? t2 : l8 == 3 ? t2 * Tn : l8 == 4 ? t2 * t2 : (t2 * t2) * Tn;
+    if (l8 >= 1 && l8 < 6) tp[l8] = pv;
+  }
+  __syncwarp();
+  if (knot || beyond) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      const int slot = (gen_next + q) & (RING_ROWS - 1);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int e = q * 16 + l8 + 8 * h;
+        double v = gcoef[e] * tp[gidx[e]];
+        if (q == 2 && h == 1 && rhs_lane) v = gsn.rn;
+        ring[slot * 16 + l8 + 8 * h] = beyond ? 0.0 : v;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int q = 0; q < 6; q++) gen_row_generic(ring, gen_next + q, n6, T1g, hs, ts, tail_s, xg, l8);
+  }
+  gsn.gen_next = gen_next + 6;
+  if (gen_next + 6 < n6 - 3) {
+    const int p = (gen_next + 3) / 6;
+    gsn.Tn = T1g[p];
+    if (rhs_lane) gsn.rn = xg[2 * p + l8 - 5];
+  }
+  __syncwarp();
+}
+
 // LU (factorizeLU, minco.hpp:99-131) fused with the forward substitution of solve() (:140-150), for the four
-// candidates of a warp at once: lanes 8c..8c+6 hold rows i % 7 of candidate c (same register pipeline as
-// topt::minco_lu_forward_t, same operations per matrix element).  n6 = 0: the group has no work.  kmax = the largest
-// n6 in the warp (loop bound, warp-uniform).  Returns true in every lane of a group whose quotients left the range of
-// the split division.
+// candidates of a warp at once: lane 8c + (i % 7) holds row i of candidate c as a 7-wide register window, the entry of
+// column j in register j % 7 (same operations per matrix element as topt::minco_lu_forward_t).  n6 = 0: the group has
+// no work.  kmax = the largest n6 in the warp (loop bound, warp-uniform).  Returns true in every lane of a group whose
+// quotients left the range of the split division.
 template <bool EXACT>
-__device__ __noinline__ bool group_lu_forward(double* gs, int n6, int kmax, const double* xg, const double* T1g, const double* hs,
-                                              const double* ts, double tail_s, double* Uf, double* Lf, double* yv) {
+__device__ __noinline__ bool group_lu_forward(double* gs, const double* gcoef, const int* gidx, int n6, int kmax, const double* xg,
+                                              const double* T1g, const double* hs, const double* ts, double tail_s, double* Uf, double* Lf,
+                                              double* yv) {
   const int lane = lane_id(), l8 = lane & 7;
   double* ring = gs;
-  double* tp = gs + 440;
-  // per-lane constants of the knot-block generator: columns l8 and l8+8 of rows gen_next + q, q = 0..5
-  double gcoef[6][2];
-  int gidx[6][2];
-#pragma unroll
-  for (int q = 0; q < 6; q++)
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int col = l8 + 8 * h;
-      const int pw = col < 13 ? g_row_pow[q][col] : -1;
-      gcoef[q][h] = pw >= 0 ? g_row_coef[q][col] : 0.0;      // structural zero: 0.0 * 1.0
-      gidx[q][h] = pw > 0 ? pw : 0;                          // index into tp[]: 0 -> 1.0
-    }
-  const bool rhs_lane = l8 == 5 || l8 == 6;                  // columns 13 / 14 of row type 2 (q = 2, h = 1): rhs = inner point p
+  double* tp = gs + 256;
   if (l8 == 0) tp[0] = 1.0;
   gen_row_generic(ring, 0, n6, T1g, hs, ts, tail_s, xg, l8);
   gen_row_generic(ring, 1, n6, T1g, hs, ts, tail_s, xg, l8);
   gen_row_generic(ring, 2, n6, T1g, hs, ts, tail_s, xg, l8);
+  GenState gsn;
+  gsn.gen_next = 3; gsn.Tn = 0.0; gsn.rn = 0.0;
+  if (3 < n6 - 3) { gsn.Tn = T1g[0]; if (l8 == 5 || l8 == 6) gsn.rn = xg[l8 - 5]; }
   __syncwarp();
-  int gen_next = 3;
-  // operands of the next knot block are fetched one block (6 pivots) ahead
-  double Tn = 0.0, rn = 0.0;
-  if (gen_next < n6 - 3) { Tn = T1g[0]; if (rhs_lane) rn = xg[l8 - 5]; }
+  gen_block(ring, tp, gcoef, gidx, gsn, n6, xg, T1g, hs, ts, tail_s);          // rows 3..8
   const bool lu_lane = l8 < 7;
   const unsigned ring_s = smem_addr(ring);
   unsigned rowp = ring_s + (lu_lane ? l8 : 0) * 128;
   unsigned nxtp = rowp + (13 - l8) * 8;
-  double wr[7], rb0 = 0.0, rb1 = 0.0;
+  double wr[7], rb0, rb1;
+#pragma unroll
+  for (int c = 0; c < 7; c++) wr[c] = lu_lane ? lds64(rowp + (c - l8 + 6) * 8) : 0.0;
+  rb0 = lds64(rowp + 13 * 8);
+  rb1 = lds64(rowp + 14 * 8);
   bool bad = false;
-  int owner = 0;
   double* Up = Uf;
   double* yp = yv;
   double* Lp = Lf + l8;
 #pragma unroll 1
-  for (int k = -1; k < kmax; k++) {
-    if (gen_next <= k + 8) {                                 // warp-uniform: rows up to k+7 are needed at pivot k
-      const bool knot = gen_next < n6 - 3;
-      const bool beyond = gen_next >= n6;                    // the whole block lies past the matrix edge: zero rows
-      if (knot) {
-        const double t2 = Tn * Tn;
-        const double pv = l8 == 1 ? Tn : l8 == 2 ? t2 : l8 == 3 ? t2 * Tn : l8 == 4 ? t2 * t2 : (t2 * t2) * Tn;
-        if (l8 >= 1 && l8 < 6) tp[l8] = pv;
-      }
-      __syncwarp();
-      if (knot || beyond) {
+  for (int k0 = 0; k0 < kmax; k0 += 7) {
 #pragma unroll
-        for (int q = 0; q < 6; q++) {
-          const int slot = (gen_next + q) & (RING_ROWS - 1);
+    for (int kk = 0; kk < 7; kk++) {
+      const int k = k0 + kk;
+      if (gsn.gen_next <= k + 8) gen_block(ring, tp, gcoef, gidx, gsn, n6, xg, T1g, hs, ts, tail_s);   // warp-uniform
+      const bool live = k < n6;
+      double u[7];
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            double v = gcoef[q][h] * tp[gidx[q][h]];
-            if (q == 2 && h == 1 && rhs_lane) v = rn;
-            ring[slot * 16 + l8 + 8 * h] = beyond ? 0.0 : v;
-          }
+      for (int c = 0; c < 7; c++) u[c] = gshfl(wr[(kk + c) % 7], kk);
+      const double y0 = gshfl(rb0, kk), y1 = gshfl(rb1, kk);
+      const double yk = rcp_refine(u[0]);
+      if (l8 == kk) {
+        if (live) {
+          stg128(Up, u[0], yk);
+          stg128(Up + 2, u[1], u[2]);
+          stg128(Up + 4, u[3], u[4]);
+          stg128(Up + 6, u[5], u[6]);
+          stg128(yp, rb0, rb1);
         }
-      } else {
-#pragma unroll 1
-        for (int q = 0; q < 6; q++) gen_row_generic(ring, gen_next + q, n6, T1g, hs, ts, tail_s, xg, l8);
+        // the owner takes row k+7: columns k+1 .. k+7 (band offsets 0..6) -> registers (kk+1+c) % 7
+        rowp = ring_s + ((k + 7) & (RING_ROWS - 1)) * 128;
+        const double2 v01 = lds128(rowp), v23 = lds128(rowp + 16), v45 = lds128(rowp + 32);
+        wr[(kk + 1) % 7] = v01.x; wr[(kk + 2) % 7] = v01.y; wr[(kk + 3) % 7] = v23.x; wr[(kk + 4) % 7] = v23.y;
+        wr[(kk + 5) % 7] = v45.x; wr[(kk + 6) % 7] = v45.y;
+        wr[kk] = lds64(rowp + 48);
+        rb0 = lds64(rowp + 13 * 8);
+        rb1 = lds64(rowp + 14 * 8);
+        nxtp = rowp + 7 * 8;
+      } else if (lu_lane) {
+        const double a = wr[kk];                             // A(myrow, k); rows past the matrix edge are all-zero
+        double l = 0.0;
+        if (a != 0.0) {
+          l = quot_spec<EXACT>(a, u[0], yk, bad);
+          // (the reference also tests A(k,j) != 0 per column; subtracting l*0 is the identity)
+#pragma unroll
+          for (int c = 1; c < 7; c++) wr[(kk + c) % 7] -= l * u[c];
+          rb0 -= l * y0;
+          rb1 -= l * y1;
+        }
+        if (live) stg64(Lp, l);
+        wr[kk] = lds64(nxtp);                                // column k+7 enters: A(myrow, k+7)
+        nxtp += 8;
       }
-      gen_next += 6;
-      if (gen_next < n6 - 3) {
-        const int p = (gen_next - 3) / 6;
-        Tn = T1g[p];
-        if (rhs_lane) rn = xg[2 * p + l8 - 5];
-      }
-      __syncwarp();
+      Up += 8; yp += 2; Lp += 8;
     }
-    if (k < 0) {                                             // prologue: rows 0..6 enter the register windows
-#pragma unroll
-      for (int c = 0; c < 7; c++) wr[c] = lu_lane ? lds64(rowp + (c - l8 + 6) * 8) : 0.0;
-      rb0 = lds64(rowp + 13 * 8);
-      rb1 = lds64(rowp + 14 * 8);
-      continue;
-    }
-    const bool live = k < n6;
-    double u[7];
-#pragma unroll
-    for (int c = 0; c < 7; c++) u[c] = gshfl(wr[c], owner);
-    const double y0 = gshfl(rb0, owner), y1 = gshfl(rb1, owner);
-    const double yk = rcp_refine(u[0]);
-    if (l8 == owner) {
-      if (live) {
-        stg128(Up, u[0], yk);
-        stg128(Up + 2, u[1], u[2]);
-        stg128(Up + 4, u[3], u[4]);
-        stg128(Up + 6, u[5], u[6]);
-        stg128(yp, rb0, rb1);
-      }
-      rowp = ring_s + ((k + 7) & (RING_ROWS - 1)) * 128;
-      const double2 v01 = lds128(rowp), v23 = lds128(rowp + 16), v45 = lds128(rowp + 32);
-      wr[0] = v01.x; wr[1] = v01.y; wr[2] = v23.x; wr[3] = v23.y; wr[4] = v45.x; wr[5] = v45.y;
-      wr[6] = lds64(rowp + 48);
-      rb0 = lds64(rowp + 13 * 8);
-      rb1 = lds64(rowp + 14 * 8);
-      nxtp = rowp + 7 * 8;
-    } else if (lu_lane) {
-      const double a = wr[0];
-      double l = 0.0;
-      if (a != 0.0) {
-        l = quot_spec<EXACT>(a, u[0], yk, bad);
-#pragma unroll
-        for (int c = 1; c < 7; c++) wr[c] -= l * u[c];
-        rb0 -= l * y0;
-        rb1 -= l * y1;
-      }
-      if (live) stg64(Lp, l);
-#pragma unroll
-      for (int c = 0; c < 6; c++) wr[c] = wr[c + 1];
-      wr[6] = lds64(nxtp);
-      nxtp += 8;
-    }
-    owner = owner == 6 ? 0 : owner + 1;
-    Up += 8; yp += 2; Lp += 8;
   }
   __syncwarp();
   const unsigned bal = __ballot_sync(FULL, bad);
   return ((bal >> (lane & ~7)) & 0xffu) != 0;
 }
 
-// 22 records [recA0, recA0+22) of A8 (8 doubles each) and 22 rhs pairs [recB0, ...) -> buf; rows outside [0, n6) read as zero
+// 18 records [recA0, recA0+18) of A8 (8 doubles each) and 18 rhs pairs [recB0, ...) -> buf; rows outside [0, n6) read as zero
 __device__ __forceinline__ void gstage(double* buf, const double* A8, const double* rhs, int recA0, int recB0, int n6, int l8) {
-#pragma unroll 1
-  for (int e = l8; e < 88; e += 8) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    const int e = l8 + 8 * i;                                 // 72 16-byte chunks of records
     const int row = recA0 + (e >> 2);
     const bool ok = row >= 0 && row < n6;
     cp_async16(buf + 2 * e, A8 + (ok ? (size_t)row * 8 + (e & 3) * 2 : 0), ok);
   }
-#pragma unroll 1
-  for (int e = l8; e < 22; e += 8) {
-    const int row = recB0 + e;
-    const bool ok = row >= 0 && row < n6;
-    cp_async16(buf + 176 + 2 * e, rhs + (ok ? 2 * (size_t)row : 0), ok);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int e = l8 + 8 * i;
+    if (e < 18) {
+      const int row = recB0 + e;
+      const bool ok = row >= 0 && row < n6;
+      cp_async16(buf + 144 + 2 * e, rhs + (ok ? 2 * (size_t)row : 0), ok);
+    }
   }
 }
 
 // Back substitution U x = y (minco.hpp:151-162): lanes 0/1 of the group = the two right-hand sides.
+// Column-oriented like the reference: x_j = b_j / U(j,j), then b_i -= U(i,j) x_j for i = j-6..j-1.
+struct BackOps { double2 d; double c1, c2, c3, c4, c5, c6, f; };
+__device__ __forceinline__ void back_load(BackOps& o, unsigned ua, unsigned fa) {
+  o.d = lds128(ua);
+  o.c1 = lds64(ua - 48); o.c2 = lds64(ua - 104); o.c3 = lds64(ua - 160); o.c4 = lds64(ua - 216); o.c5 = lds64(ua - 272);
+  o.c6 = lds64(ua - 328); o.f = lds64(fa);
+}
 template <bool EXACT>
 __device__ __noinline__ bool group_back(double* gs, int n6, int kmax, const double* Uf, const double* __restrict__ y, double* __restrict__ x) {
   const int lane = lane_id(), l8 = lane & 7;
@@ -293,33 +321,32 @@ __device__ __noinline__ bool group_back(double* gs, int n6, int kmax, const doub
     __syncwarp();
     gstage(gs + (cur ^ 1) * SB, Uf, y, c0 - CH - 6, c0 - CH - 6, c0 > 0 ? n6 : 0, l8);
     if (act && c0 >= 0) {
-      const int rows = min(CH, n6 - c0);
-      unsigned ua = S_s + (cur * SB + (rows + 5) * 8) * 8;
-      unsigned fa = S_s + (cur * SB + 176 + 2 * (rows - 1) + l8) * 8;
+      const int rows = min(CH, n6 - c0);                     // even (n6 and CH are multiples of 6)
+      unsigned ua = S_s + (cur * SB + (rows + 5) * 8) * 8;   // record of row j = c0 + i
+      unsigned fa = S_s + (cur * SB + 144 + 2 * (rows - 1) + l8) * 8;
       double* xo = x + 2 * (c0 + rows - 1) + l8;
-      double2 nd = lds128(ua);
-      double n1 = lds64(ua - 48), n2 = lds64(ua - 104), n3 = lds64(ua - 160), n4 = lds64(ua - 216), n5 = lds64(ua - 272),
-             n6_ = lds64(ua - 328), nf = lds64(fa);
-#pragma unroll 1
-      for (int i = rows - 1; i >= 0; i--) {
-        const double2 cd = nd;
-        const double c1 = n1, c2 = n2, c3 = n3, c4 = n4, c5 = n5, c6 = n6_, cfr = nf;
-        ua -= 64; fa -= 16;
-        if (i > 0) {
-          nd = lds128(ua);
-          n1 = lds64(ua - 48); n2 = lds64(ua - 104); n3 = lds64(ua - 160); n4 = lds64(ua - 216); n5 = lds64(ua - 272);
-          n6_ = lds64(ua - 328); nf = lds64(fa);
-        }
-        const double xv = quot_spec<EXACT>(a0, cd.x, cd.y, bad);
-        stg64(xo, xv);
-        xo -= 2;
-        a0 = a1 - c1 * xv;
-        a1 = a2 - c2 * xv;
-        a2 = a3 - c3 * xv;
-        a3 = a4 - c4 * xv;
-        a4 = a5 - c5 * xv;
-        a5 = cfr - c6 * xv;
+      BackOps A, B;
+      back_load(A, ua, fa);
+#define ALORE_BACK_STEP(CUR, NXT, more)                                        \
+      {                                                                        \
+        ua -= 64; fa -= 16;                                                    \
+        if (more) back_load(NXT, ua, fa);                                      \
+        const double xv = quot_spec<EXACT>(a0, CUR.d.x, CUR.d.y, bad);         \
+        stg64(xo, xv);                                                         \
+        xo -= 2;                                                               \
+        a0 = a1 - CUR.c1 * xv;                                                 \
+        a1 = a2 - CUR.c2 * xv;                                                 \
+        a2 = a3 - CUR.c3 * xv;                                                 \
+        a3 = a4 - CUR.c4 * xv;                                                 \
+        a4 = a5 - CUR.c5 * xv;                                                 \
+        a5 = CUR.f - CUR.c6 * xv;                                              \
       }
+#pragma unroll 1
+      for (int i = rows; i > 0; i -= 2) {
+        ALORE_BACK_STEP(A, B, true)
+        ALORE_BACK_STEP(B, A, i > 2)
+      }
+#undef ALORE_BACK_STEP
     }
     __syncwarp();
     cur ^= 1;
@@ -330,7 +357,11 @@ __device__ __noinline__ bool group_back(double* gs, int n6, int kmax, const doub
   return ((bal >> (lane & ~7)) & 0xffu) != 0;
 }
 
-// U^T z = b ascending (minco.hpp:170-183)
+// U^T z = b ascending (minco.hpp:170-183): z_j = b_j / U(j,j), then b_i -= U(j,i) z_j, i = j+1..j+6.
+struct UpOps { double2 r01, r23, r45, r67; double f; };
+__device__ __forceinline__ void up_load(UpOps& o, unsigned ua, unsigned fa) {
+  o.r01 = lds128(ua); o.r23 = lds128(ua + 16); o.r45 = lds128(ua + 32); o.r67 = lds128(ua + 48); o.f = lds64(fa);
+}
 template <bool EXACT>
 __device__ __noinline__ bool group_adj_upper(double* gs, int n6, int kmax, const double* Uf, const double* __restrict__ b, double* __restrict__ z) {
   const int lane = lane_id(), l8 = lane & 7;
@@ -347,28 +378,32 @@ __device__ __noinline__ bool group_adj_upper(double* gs, int n6, int kmax, const
     __syncwarp();
     gstage(gs + (cur ^ 1) * SB, Uf, b, c0 + CH, c0 + CH + 6, n6, l8);
     if (act && c0 < n6) {
-      const int rows = min(CH, n6 - c0);
+      const int rows = min(CH, n6 - c0);                     // even
       unsigned ua = S_s + (cur * SB) * 8;
-      unsigned fa = S_s + (cur * SB + 176 + l8) * 8;
+      unsigned fa = S_s + (cur * SB + 144 + l8) * 8;
       double* zo = z + 2 * c0 + l8;
-      double2 n01 = lds128(ua), n23 = lds128(ua + 16), n45 = lds128(ua + 32), n67 = lds128(ua + 48);
-      double nf = lds64(fa);
-#pragma unroll 1
-      for (int i = 0; i < rows; i++) {
-        const double2 c01 = n01, c23 = n23, c45 = n45, c67 = n67;
-        const double cfr = nf;
-        ua += 64; fa += 16;
-        if (i + 1 < rows) { n01 = lds128(ua); n23 = lds128(ua + 16); n45 = lds128(ua + 32); n67 = lds128(ua + 48); nf = lds64(fa); }
-        const double zv = quot_spec<EXACT>(a0, c01.x, c01.y, bad);
-        stg64(zo, zv);
-        zo += 2;
-        a0 = a1 - c23.x * zv;
-        a1 = a2 - c23.y * zv;
-        a2 = a3 - c45.x * zv;
-        a3 = a4 - c45.y * zv;
-        a4 = a5 - c67.x * zv;
-        a5 = cfr - c67.y * zv;
+      UpOps A, B;
+      up_load(A, ua, fa);
+#define ALORE_UP_STEP(CUR, NXT, more)                                          \
+      {                                                                        \
+        ua += 64; fa += 16;                                                    \
+        if (more) up_load(NXT, ua, fa);                                        \
+        const double zv = quot_spec<EXACT>(a0, CUR.r01.x, CUR.r01.y, bad);     \
+        stg64(zo, zv);                                                         \
+        zo += 2;                                                               \
+        a0 = a1 - CUR.r23.x * zv;                                              \
+        a1 = a2 - CUR.r23.y * zv;                                              \
+        a2 = a3 - CUR.r45.x * zv;                                              \
+        a3 = a4 - CUR.r45.y * zv;                                              \
+        a4 = a5 - CUR.r67.x * zv;                                              \
+        a5 = CUR.f - CUR.r67.y * zv;                                           \
       }
+#pragma unroll 1
+      for (int i = rows; i > 0; i -= 2) {
+        ALORE_UP_STEP(A, B, true)
+        ALORE_UP_STEP(B, A, i > 2)
+      }
+#undef ALORE_UP_STEP
     }
     __syncwarp();
     cur ^= 1;
@@ -379,7 +414,12 @@ __device__ __noinline__ bool group_adj_upper(double* gs, int n6, int kmax, const
   return ((bal >> (lane & ~7)) & 0xffu) != 0;
 }
 
-// L^T x = z descending (minco.hpp:184-196); L(j,i) = Lf[8i + j % 7]
+// L^T x = z descending (minco.hpp:184-196): b_i -= L(j,i) b_j for i = j-6..j-1; L(j,i) = Lf[8i + j % 7]
+struct LowOps { double c1, c2, c3, c4, c5, c6, f; };
+__device__ __forceinline__ void low_load(LowOps& o, unsigned la, unsigned fa) {
+  o.c1 = lds64(la - 64); o.c2 = lds64(la - 128); o.c3 = lds64(la - 192); o.c4 = lds64(la - 256); o.c5 = lds64(la - 320);
+  o.c6 = lds64(la - 384); o.f = lds64(fa);
+}
 __device__ __noinline__ void group_adj_lower(double* gs, int n6, int kmax, const double* Lf, const double* __restrict__ z, double* __restrict__ x) {
   const int lane = lane_id(), l8 = lane & 7;
   const unsigned S_s = smem_addr(gs);
@@ -398,33 +438,35 @@ __device__ __noinline__ void group_adj_lower(double* gs, int n6, int kmax, const
     __syncwarp();
     gstage(gs + (cur ^ 1) * SB, Lf, z, c0 - CH - 6, c0 - CH - 6, c0 > 0 ? n6 : 0, l8);
     if (act && c0 >= 0) {
-      const int rows = min(CH, n6 - c0);
+      const int rows = min(CH, n6 - c0);                     // even
       int jm = (c0 + rows - 1) % 7;
-      unsigned la = S_s + (cur * SB + (rows + 5) * 8 + jm) * 8;
-      unsigned fa = S_s + (cur * SB + 176 + 2 * (rows - 1) + l8) * 8;
+      unsigned la = S_s + (cur * SB + (rows + 5) * 8 + jm) * 8;   // record of column j = c0 + i, slot j % 7
+      unsigned fa = S_s + (cur * SB + 144 + 2 * (rows - 1) + l8) * 8;
       double* xo = x + 2 * (c0 + rows - 1) + l8;
-      double n1 = lds64(la - 64), n2 = lds64(la - 128), n3 = lds64(la - 192), n4 = lds64(la - 256), n5 = lds64(la - 320),
-             n6_ = lds64(la - 384), nf = lds64(fa);
-#pragma unroll 1
-      for (int i = rows - 1; i >= 0; i--) {
-        const double c1 = n1, c2 = n2, c3 = n3, c4 = n4, c5 = n5, c6 = n6_, cfr = nf;
-        la -= (jm == 0) ? (64 - 48) : (64 + 8);
-        jm = jm == 0 ? 6 : jm - 1;
-        fa -= 16;
-        if (i > 0) {
-          n1 = lds64(la - 64); n2 = lds64(la - 128); n3 = lds64(la - 192); n4 = lds64(la - 256); n5 = lds64(la - 320);
-          n6_ = lds64(la - 384); nf = lds64(fa);
-        }
-        const double xv = a0;
-        stg64(xo, xv);
-        xo -= 2;
-        a0 = a1 - c1 * xv;
-        a1 = a2 - c2 * xv;
-        a2 = a3 - c3 * xv;
-        a3 = a4 - c4 * xv;
-        a4 = a5 - c5 * xv;
-        a5 = cfr - c6 * xv;
+      LowOps A, B;
+      low_load(A, la, fa);
+#define ALORE_LOW_STEP(CUR, NXT, more)                                         \
+      {                                                                        \
+        la -= (jm == 0) ? (64 - 48) : (64 + 8);                                \
+        jm = jm == 0 ? 6 : jm - 1;                                             \
+        fa -= 16;                                                              \
+        if (more) low_load(NXT, la, fa);                                       \
+        const double xv = a0;                                                  \
+        stg64(xo, xv);                                                         \
+        xo -= 2;                                                               \
+        a0 = a1 - CUR.c1 * xv;                                                 \
+        a1 = a2 - CUR.c2 * xv;                                                 \
+        a2 = a3 - CUR.c3 * xv;                                                 \
+        a3 = a4 - CUR.c4 * xv;                                                 \
+        a4 = a5 - CUR.c5 * xv;                                                 \
+        a5 = CUR.f - CUR.c6 * xv;                                              \
       }
+#pragma unroll 1
+      for (int i = rows; i > 0; i -= 2) {
+        ALORE_LOW_STEP(A, B, true)
+        ALORE_LOW_STEP(B, A, i > 2)
+      }
+#undef ALORE_LOW_STEP
     }
     __syncwarp();
     cur ^= 1;
@@ -446,6 +488,10 @@ wave_solve_kernel(const __grid_constant__ WParams kp, BatchDev bt, WaveDev wd, i
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, grp = lane >> 3;
   double* gs = smem + (size_t)(wib * 4 + grp) * GS;
+  double* gcoef = smem + (size_t)SOLVE_WARPS * 4 * GS;
+  int* gidx = reinterpret_cast<int*>(gcoef + GTAB);
+  gen_table_init(gcoef, gidx);
+  __syncthreads();
   const int* list = cur ? wd.list1 : wd.list0;
   const int nact = wd.count[cur];
   if (blockIdx.x == 0 && threadIdx.x == 0) wd.count[cur ^ 1] = 0;    // the step kernel of this round appends there
@@ -474,10 +520,10 @@ wave_solve_kernel(const __grid_constant__ WParams kp, BatchDev bt, WaveDev wd, i
     const double tail_s = n6 ? xg[2 * (N - 1)] : 0.0;
     bool bad = g_force_exact_div != 0;
     const long long t0 = clock64();
-    if (!bad) bad = group_lu_forward<false>(gs, n6, kmax, xg, T1g, hs, ts, tail_s, Ug, Lg, yg);
+    if (!bad) bad = group_lu_forward<false>(gs, gcoef, gidx, n6, kmax, xg, T1g, hs, ts, tail_s, Ug, Lg, yg);
     if (__any_sync(FULL, bad)) {                                      // rare: redo the affected groups with the compiler's division
       const int n6x = bad ? n6 : 0;
-      group_lu_forward<true>(gs, n6x, warp_max_i(n6x), xg, T1g, hs, ts, tail_s, Ug, Lg, yg);
+      group_lu_forward<true>(gs, gcoef, gidx, n6x, warp_max_i(n6x), xg, T1g, hs, ts, tail_s, Ug, Lg, yg);
       WDBG_ADD(3, 1);
     }
     const long long t1 = clock64();
