@@ -442,6 +442,7 @@ int max_pieces(const int32_t* po, int B) {
 
 }  // namespace
 
+static void lpt_order(const std::vector<int32_t>& po, const int32_t* evals, std::vector<int>& order);
 struct alore_batch {
   alore_ctx* ctx = nullptr;
   int B = 0, tot = 0, Nmax = 0;
@@ -836,13 +837,30 @@ int alore_batch_upload(alore_ctx* ctx, const alore_candidates_t* c, alore_batch*
 int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, void* cuda_stream) {
   if (!ctx || !prm || !bh) return ALORE_EINVAL;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-  if (getenv("ALORE_LEGACY_OPT")) {                 // round-1 persistent kernel (kept for A/B timing during development)
+  // Two implementations of the same computation, bit-identical results (scripts/opt_ab.py):
+  //  * persistent (default): one warp per candidate, asynchronous, longest-predicted-work first — faster whenever the
+  //    makespan is set by the heaviest candidate (it starts first and overlaps everything else);
+  //  * wavefront (ALORE_OPT_WAVE=1): lockstep rounds of small kernels (wave_opt.cuh) — fewer instructions in total and
+  //    independent of any schedule prediction, but every candidate advances at the pace of the round.
+  if (!getenv("ALORE_OPT_WAVE")) {
     Launch L;
     int rc = prepare_launch(ctx, prm, bh->Nmax, bh->B, opt_kernel, L, true);
     if (rc) return rc;
+    if (bh->runs > 0) {   // a resident batch that is optimised again: longest predicted work (pieces x previous evaluations) first
+      std::vector<int32_t> ev(bh->B);
+      ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), bh->res.evals, bh->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+      std::vector<int> order;
+      lpt_order(bh->piece_off, ev.data(), order);
+      ALORE_CUDA(ctx, cudaMemcpyAsync(bh->d_order, order.data(), bh->B * sizeof(int), cudaMemcpyHostToDevice, st));
+      ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+      ctx->sched_piece_off = bh->piece_off;
+      ctx->sched_evals = ev;
+    }
     bh->runs++;
     ALORE_CUDA(ctx, cudaMemsetAsync(L.counter, 0, sizeof(int), st));
     ALORE_CUDA(ctx, cudaEventRecord(bh->e0, st));
+    set_l2_window(ctx, st, L.slabs, (size_t)L.slots * L.kp.L.total * sizeof(double));
     opt_kernel<<<L.slots, 32, L.smem, st>>>(L.kp, bh->bt, bh->res, L.slabs, L.hists, L.counter);
     ctx->launches++;
     ALORE_CUDA(ctx, cudaGetLastError());
@@ -865,7 +883,13 @@ int alore_batch_download(alore_ctx* ctx, alore_batch* bh, alore_results_t* out) 
   DN(out->evals, r.evals, B) DN(out->cost, r.cost, B) DN(out->inner_pts, r.inner_pts, 2 * (size_t)(tot - B))
   DN(out->tail_s, r.tail_s, B) DN(out->piece_T, r.piece_T, tot) DN(out->coeffs, r.coeffs, 12 * (size_t)tot)
 #undef DN
-  ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+  {
+    std::vector<int32_t> ev(B);
+    ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), r.evals, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->sched_piece_off = bh->piece_off;
+    ctx->sched_evals.swap(ev);
+  }
   cudaEventElapsedTime(&bh->kernel_ms, bh->e0, bh->e1);
   (void)cudaGetLastError();
   return ALORE_OK;
@@ -965,7 +989,7 @@ int alore_cost_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_cand
   if (safe_dis) { TRY(dev_copy(ctx, &d_sd, safe_dis, (size_t)B, st)) }
   TRY(dev_copy(ctx, &d_cost, (const double*)nullptr, (size_t)B, st))
   TRY(dev_copy(ctx, &d_err, (const double*)nullptr, 2 * (size_t)B, st))
-  if (getenv("ALORE_LEGACY_OPT")) {
+  if (getenv("ALORE_COST_PERSISTENT")) {
     TRY(prepare_launch(ctx, prm, bh->Nmax, B, cost_kernel, L, false))
     cudaMemsetAsync(L.counter, 0, sizeof(int), st);
     cudaMemsetAsync(d_err, 0, 2 * (size_t)B * sizeof(double), st);

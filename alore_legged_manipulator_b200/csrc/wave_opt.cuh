@@ -28,6 +28,10 @@ namespace wave {
 using namespace topt;
 
 enum { PH_NEW = 0, PH_INIT = 1, PH_LS = 2, PH_FINAL = 3, PH_DONE = 4 };
+#ifndef ALORE_TL_NB
+#define ALORE_TL_NB 4
+#endif
+constexpr int TL_NB = ALORE_TL_NB;   // history pairs in flight (power of two): the recursion is bound by (memory latency) / TL_NB
 
 // Developer counters (alore_debug_wave_counters): [0] LU warp-cycles, [1] back-substitution warp-cycles, [2] LU warps,
 // [3] exact-division reruns of the LU, [4] of the back substitution, [5] of the adjoint, [6] adjoint-upper warp-cycles,
@@ -679,7 +683,7 @@ wave_penalty_kernel(const __grid_constant__ WParams kp, BatchDev bt, WaveDev wd,
 // =====================================================================================================
 __host__ __device__ inline size_t step_smem_doubles(int Nmax) {
   const size_t npad = (size_t)((3 * Nmax) & ~1);
-  return (size_t)Nmax + (Nmax + 1) + 3 + 2 + npad + 4 * (2 * npad + 4) + 8;
+  return (size_t)Nmax + (Nmax + 1) + 3 + 2 + (TL_NB + 2) + npad + (TL_NB > 4 ? TL_NB : 4) * (2 * npad + 4) + 8;
 }
 
 // tail of costFunctionCallback[Path] (optimizer.cpp:675-689 / 1299-1315): adjoint -> gradient w.r.t. points, tail s, tau
@@ -734,129 +738,144 @@ __device__ __forceinline__ double assemble_gradient(const Warp& w, const alore_p
   return f_partial + (stage == 1 ? time_weight : P.ppw_time) * tsum;
 }
 
-// Two-loop recursion (lbfgs.hpp:716-741) with the search direction held in REGISTERS: lane l owns elements l + 32 q,
-// q < EPL (the same ownership as topt::lbfgs_two_loop, so every partial sum, the butterfly and every update are the
-// same operations in the same order), loops fully unrolled, butterfly inline.  ~85 instructions per history step
-// instead of ~350: the recursion is a chain of dependent issues, so its time is its instruction count.
-// History pairs stream HBM -> L2 (prefetch 12 steps ahead) -> 4-deep cp.async ring -> registers.
+// The same recursion with the history pairs moved by TMA: ONE lane issues two 1-D bulk copies per pair
+// (cp.async.bulk, completion counted on an mbarrier) instead of every lane issuing cp.async chunks and computing their
+// addresses — the staging drops from ~50 to ~12 warp-instructions per step; the consumers wait on the barrier's
+// phase.  mb = 4 mbarriers + a phase word in shared memory (initialised once per kernel by two_loop_tma_init).
+__device__ __forceinline__ void two_loop_tma_init(double* mbar) {
+  if (lane_id() == 0) {
+    const unsigned b0 = smem_addr(mbar);
+    for (int i = 0; i < TL_NB; i++) mbar_init(b0 + 8 * i, 1);
+    reinterpret_cast<int*>(mbar + TL_NB)[0] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
 template <int EPL>
-__device__ __noinline__ void two_loop_reg(Warp& w, int m, int end, int bound, double ys, double yy) {
-  constexpr int NB = 4, PF = 12;
+__device__ __noinline__ void two_loop_tma(Warp& w, int m, int end, int bound, double ys, double yy) {
+  constexpr int NB = TL_NB, PF = 16;
   const int n = w.n, lane = w.lane, np = w.npad, hs = np + 4, bs = 2 * np + 4;
   double* dsh = as_shared(w.d);
   double* H = as_shared(w.hbuf);
   double* lm_s = as_global(w.lm_s);
   const double* lm_y = as_global(w.lm_y);
-  const int nchunk = np + 2;                         // 16-byte chunks of one pair: (np + 4) / 2 of the s-record, np / 2 of y
-  const int schunk = (np + 4) >> 1;
-  auto stage = [&](int slot, int jj, bool valid) {
-    if (valid) {
-      double* dst = H + (size_t)slot * bs;
-      const double* sg = lm_s + (size_t)jj * hs;
-      const double* yg = lm_y + (size_t)jj * np;
-#pragma unroll
-      for (int c = 0; c < EPL + 1; c++) {
-        const int ch = lane + 32 * c;
-        if (ch < nchunk) cp_async16(dst + 2 * ch, ch < schunk ? sg + 2 * ch : yg + 2 * (ch - schunk), true);
-      }
+  const unsigned H_s = smem_addr(H), bar0 = smem_addr(w.mbar);
+  int* phw = reinterpret_cast<int*>(as_shared(w.mbar) + TL_NB);
+  unsigned ph = (unsigned)*phw;
+  auto issue = [&](int stage, int jj) {
+    if (lane == 0) {
+      const unsigned bar = bar0 + 8 * stage, dst = H_s + (unsigned)(stage * bs) * 8;
+      mbar_expect_tx(bar, (unsigned)(hs + np) * 8);
+      tma_load_1d(dst, lm_s + (size_t)jj * hs, (unsigned)hs * 8, bar);
+      tma_load_1d(dst + (unsigned)hs * 8, lm_y + (size_t)jj * np, (unsigned)np * 8, bar);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto prefetch = [&](int jj) {                      // one 128-byte line per lane: s-record then y-record
+  auto wait = [&](int stage) {
+    mbar_wait(bar0 + 8 * stage, (ph >> stage) & 1u);
+    ph ^= 1u << stage;
+  };
+  auto prefetch = [&](int jj) {                      // one 128-byte line per lane: s-record then y-record (HBM -> L2)
     const int line = lane * 16;
     if (line < hs) prefetch_l2(lm_s + (size_t)jj * hs + line);
     if (line < np) prefetch_l2(lm_y + (size_t)jj * np + line);
-    if (EPL > 4) {
-      if (line + 512 < hs) prefetch_l2(lm_s + (size_t)jj * hs + line + 512);
-      if (line + 512 < np) prefetch_l2(lm_y + (size_t)jj * np + line + 512);
-    }
   };
   double d[EPL];
 #pragma unroll
   for (int q = 0; q < EPL; q++) d[q] = (lane + 32 * q < n) ? dsh[lane + 32 * q] : 0.0;
   const bool last_ok = lane + 32 * (EPL - 1) < n;    // only the last element of a lane can lie past n
+  asm volatile("fence.proxy.async;" ::: "memory");   // the newest pair was written with ordinary stores
+  __syncwarp();
   int j = end, jn = end, jp = end;
 #pragma unroll 1
   for (int a = 0; a < PF; a++) { jp = jp == 0 ? m - 1 : jp - 1; if (a < bound) prefetch(jp); }
 #pragma unroll 1
-  for (int a = 0; a < NB - 1; a++) { jn = jn == 0 ? m - 1 : jn - 1; stage(a, jn, a < bound); }
+  for (int a = 0; a < NB - 1; a++) { jn = jn == 0 ? m - 1 : jn - 1; if (a < bound) issue(a, jn); }
 #pragma unroll 1
   for (int it = 0; it < bound; ++it) {
     j = j == 0 ? m - 1 : j - 1;
-    asm volatile("cp.async.wait_group %0;" ::"n"(NB - 2) : "memory");
-    __syncwarp();
+    wait(it & (NB - 1));
+    __syncwarp();                                    // every lane has left the buffer that is refilled next
     jn = jn == 0 ? m - 1 : jn - 1;
-    stage((it + NB - 1) & (NB - 1), jn, it + NB - 1 < bound);
+    if (it + NB - 1 < bound) issue((it + NB - 1) & (NB - 1), jn);
     jp = jp == 0 ? m - 1 : jp - 1;
     if (it + PF < bound) prefetch(jp);
-    const double* sj = H + (size_t)(it & (NB - 1)) * bs;
-    const double* yj = sj + hs;
+    // explicit shared-space addresses: through the dynamic stage index the compiler would fall back to generic loads
+    const unsigned sj = H_s + (unsigned)((it & (NB - 1)) * bs + lane) * 8;
+    const unsigned yj = sj + (unsigned)hs * 8;
+    double sv[EPL], yv[EPL];
+#pragma unroll
+    for (int q = 0; q < EPL; q++) { sv[q] = (q < EPL - 1 || last_ok) ? lds64(sj + 256 * q) : 0.0; yv[q] = (q < EPL - 1 || last_ok) ? lds64(yj + 256 * q) : 0.0; }
+    const double2 yr = lds128(sj + (unsigned)(np - lane) * 8);
     double ps = 0.0;
 #pragma unroll
     for (int q = 0; q < EPL; q++)
-      if (q < EPL - 1 || last_ok) ps += sj[lane + 32 * q] * d[q];
+      if (q < EPL - 1 || last_ok) ps += sv[q] * d[q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ps += shfl_xor_d(ps, o);
-    const double2 yr = *reinterpret_cast<const double2*>(sj + np);
     const double alpha = div_rcp(ps, yr.x, yr.y);
-    if (lane == 0) lm_s[(size_t)j * hs + np + 2] = alpha;
+    if (lane == 0) stg64(lm_s + (size_t)j * hs + np + 2, alpha);
     const double c = -alpha;
 #pragma unroll
     for (int q = 0; q < EPL; q++)
-      if (q < EPL - 1 || last_ok) d[q] += c * yj[lane + 32 * q];
+      if (q < EPL - 1 || last_ok) d[q] += c * yv[q];
   }
   {
     const double c = ys / yy;
 #pragma unroll
     for (int q = 0; q < EPL; q++) d[q] *= c;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();   // alpha_j written by lane 0 above travels back with the s-records below; all staging buffers are free
+  asm volatile("fence.proxy.async;" ::: "memory");   // alpha_j (ordinary stores by lane 0) travels back with the s-records
+  __syncwarp();
   jn = j == 0 ? m - 1 : j - 1;
   jp = jn;
 #pragma unroll 1
   for (int a = 0; a < PF; a++) { jp = jp == m - 1 ? 0 : jp + 1; if (a < bound) prefetch(jp); }
 #pragma unroll 1
-  for (int a = 0; a < NB - 1; a++) { jn = jn == m - 1 ? 0 : jn + 1; stage(a, jn, a < bound); }
+  for (int a = 0; a < NB - 1; a++) { jn = jn == m - 1 ? 0 : jn + 1; if (a < bound) issue(a, jn); }
 #pragma unroll 1
   for (int it = 0; it < bound; ++it) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(NB - 2) : "memory");
+    wait(it & (NB - 1));
     __syncwarp();
     jn = jn == m - 1 ? 0 : jn + 1;
-    stage((it + NB - 1) & (NB - 1), jn, it + NB - 1 < bound);
+    if (it + NB - 1 < bound) issue((it + NB - 1) & (NB - 1), jn);
     jp = jp == m - 1 ? 0 : jp + 1;
     if (it + PF < bound) prefetch(jp);
-    const double* sj = H + (size_t)(it & (NB - 1)) * bs;
-    const double* yj = sj + hs;
+    const unsigned sj = H_s + (unsigned)((it & (NB - 1)) * bs + lane) * 8;
+    const unsigned yj = sj + (unsigned)hs * 8;
+    double sv[EPL], yv[EPL];
+#pragma unroll
+    for (int q = 0; q < EPL; q++) { sv[q] = (q < EPL - 1 || last_ok) ? lds64(sj + 256 * q) : 0.0; yv[q] = (q < EPL - 1 || last_ok) ? lds64(yj + 256 * q) : 0.0; }
+    const double2 yr = lds128(sj + (unsigned)(np - lane) * 8);
+    const double aj = lds64(sj + (unsigned)(np + 2 - lane) * 8);
     double ps = 0.0;
 #pragma unroll
     for (int q = 0; q < EPL; q++)
-      if (q < EPL - 1 || last_ok) ps += yj[lane + 32 * q] * d[q];
+      if (q < EPL - 1 || last_ok) ps += yv[q] * d[q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ps += shfl_xor_d(ps, o);
-    const double2 yr = *reinterpret_cast<const double2*>(sj + np);
     const double beta = div_rcp(ps, yr.x, yr.y);
-    const double c = sj[np + 2] - beta;
+    const double c = aj - beta;
 #pragma unroll
     for (int q = 0; q < EPL; q++)
-      if (q < EPL - 1 || last_ok) d[q] += c * sj[lane + 32 * q];
+      if (q < EPL - 1 || last_ok) d[q] += c * sv[q];
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int q = 0; q < EPL; q++)
     if (lane + 32 * q < n) dsh[lane + 32 * q] = d[q];
   __syncwarp();
+  if (lane == 0) *phw = (int)ph;
+  __syncwarp();
 }
 __device__ __forceinline__ void two_loop_dispatch(Warp& w, int m, int end, int bound, double ys, double yy) {
   switch ((w.n + 31) >> 5) {
-    case 1: two_loop_reg<1>(w, m, end, bound, ys, yy); break;
-    case 2: two_loop_reg<2>(w, m, end, bound, ys, yy); break;
-    case 3: two_loop_reg<3>(w, m, end, bound, ys, yy); break;
-    case 4: two_loop_reg<4>(w, m, end, bound, ys, yy); break;
-    case 5: two_loop_reg<5>(w, m, end, bound, ys, yy); break;
-    case 6: two_loop_reg<6>(w, m, end, bound, ys, yy); break;
-    case 7: two_loop_reg<7>(w, m, end, bound, ys, yy); break;
-    case 8: two_loop_reg<8>(w, m, end, bound, ys, yy); break;
+    case 1: two_loop_tma<1>(w, m, end, bound, ys, yy); break;
+    case 2: two_loop_tma<2>(w, m, end, bound, ys, yy); break;
+    case 3: two_loop_tma<3>(w, m, end, bound, ys, yy); break;
+    case 4: two_loop_tma<4>(w, m, end, bound, ys, yy); break;
+    case 5: two_loop_tma<5>(w, m, end, bound, ys, yy); break;
+    case 6: two_loop_tma<6>(w, m, end, bound, ys, yy); break;
+    case 7: two_loop_tma<7>(w, m, end, bound, ys, yy); break;
+    case 8: two_loop_tma<8>(w, m, end, bound, ys, yy); break;
     default: lbfgs_two_loop(w, m, end, bound, ys, yy); break;    // very long trajectories: the rolled version
   }
 }
@@ -894,6 +913,7 @@ __device__ __noinline__ bool step_candidate(const WParams& kp, const BatchDev& b
     double* q = smem;
     w.T1 = q; q += kp.Nmax; w.sumT = q; q += kp.Nmax + 1 + 3;
     q = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15));
+    w.mbar = q; q += TL_NB + 2;
     w.d = q; q += kp.npadmax;
     w.hbuf = q; w.stg = q;
   }
@@ -1178,6 +1198,11 @@ wave_step_kernel(const __grid_constant__ WParams kp, BatchDev bt, ResultDev out,
   const int* list = cur ? wd.list1 : wd.list0;
   int* nlist = cur ? wd.list0 : wd.list1;
   const int nact = wd.count[cur];
+  {
+    double* q = smem + kp.Nmax + kp.Nmax + 1 + 3;
+    q = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15));
+    two_loop_tma_init(q);                            // the mbarriers of the history pipeline (same carve as step_candidate)
+  }
 #pragma unroll 1
   for (int slot = blockIdx.x; slot < nact; slot += gridDim.x) {
     const int b = list[slot];

@@ -5,6 +5,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np
+import os
+os.environ["ALORE_OPT_WAVE"] = "1"
 import alore_legged_manipulator_b200 as alore
 from alore_legged_manipulator_b200.ms_planner import DeviceBatch, MSPlanner
 import bench

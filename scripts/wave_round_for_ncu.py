@@ -3,6 +3,8 @@ import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+import os
+os.environ["ALORE_OPT_WAVE"] = "1"
 import alore_legged_manipulator_b200 as alore
 from alore_legged_manipulator_b200.ms_planner import DeviceBatch
 import bench
