@@ -362,6 +362,32 @@ int orc_lbfgs_run(int kind, int n, double* x, const alore_lbfgs_params_t* param,
   return ret;
 }
 
+// ---- pieces exposed only so that tests/test_ref_pins.py can compare them with the reference-compiled fragments ----
+// BandedSystem (minco.hpp:43-198) on a dense row-major N x N matrix, rhs b [N][2]; mode 0 solve, 1 solveAdj.
+int orc_banded(int N, int p, int q, const double* A, double* b, int mode, double* band_out) {
+  BandedSystem bs;
+  bs.create(N, p, q);
+  for (int i = 0; i < N; i++)
+    for (int j = std::max(0, i - p); j <= std::min(N - 1, i + q); j++) bs(i, j) = A[(size_t)i * N + j];
+  bs.factorizeLU();
+  if (mode == 0) bs.solve(b);
+  else bs.solveAdj(b);
+  if (band_out) std::memcpy(band_out, bs.ptrData.data(), bs.ptrData.size() * sizeof(double));
+  return 0;
+}
+// which: 0 RealT2VirtualT, 1 VirtualT2RealT, 2 backwardGradT (optimizer.cpp:573-591, 1088-1106)
+void orc_tmaps(int n, const double* in, int which, const double* gradT, double* out) {
+  Vec a(in, in + n), o;
+  if (which == 0) MSPlanner::RealT2VirtualT(a, out);
+  else if (which == 1) { MSPlanner::VirtualT2RealT(in, n, o); std::memcpy(out, o.data(), n * sizeof(double)); }
+  else { Vec g(gradT, gradT + n); MSPlanner::backwardGradT(in, g, out); }
+}
+void orc_smoothed_l1(double eps, double x, double* f, double* df) {   // optimizer.cpp:1069-1086
+  MSPlanner pl;
+  pl.p.smoothEps = eps;
+  pl.positiveSmoothedL1(x, *f, *df);
+}
+
 void orc_set_exact_chain_weights(int on) { orc::g_exact_chain_weights = on != 0; }
 
 void orc_set_trig_portable(int on) { orc::g_trig_portable = on != 0; }
