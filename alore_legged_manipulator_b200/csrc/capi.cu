@@ -156,6 +156,8 @@ static int ensure_map(alore_ctx* ctx, const alore_map_geom_t* geom, bool force_f
     ctx->have_map = false;
     ALORE_CUDA(ctx, cudaMalloc(&ctx->d_occ, cells));
     ALORE_CUDA(ctx, cudaMalloc(&ctx->d_dist, cells * sizeof(double)));
+    // rows no alore_esdf_update has uploaded yet read as Unknown, the state SDFmap's constructor gives gridmap_
+    ALORE_CUDA(ctx, cudaMemsetAsync(ctx->d_occ, ALORE_UNKNOWN, cells, ctx->stream));
     ctx->map_cells = cells;
     force_fill = true;
   }
@@ -184,7 +186,7 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
   ALORE_CUDA(ctx, cudaMemcpyAsync(ctx->d_occ + (size_t)min_x * gly, occ + (size_t)min_x * gly, (size_t)NX * gly,
                                   cudaMemcpyHostToDevice, st));
   ALORE_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  rc = alore_esdf_run(ctx, ctx->d_occ, ctx->d_dist, min_x, min_y, max_x, max_y, ref_compat, st, nullptr, nullptr);
+  rc = alore_esdf_run(ctx, &ctx->geom, ctx->d_occ, ctx->d_dist, min_x, min_y, max_x, max_y, ref_compat, st, nullptr, nullptr);
   if (rc) return rc;
   ALORE_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
   // D2H: exactly the rectangle the reference writes.
@@ -207,17 +209,23 @@ int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const ui
   ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool resident = (d_occ == nullptr && d_dist_inout == nullptr);
   if (resident) {
-    // HBM-resident path: rebuild the context's own ESDF from the occupancy grid a previous alore_esdf_update left on the device
+    // HBM-resident path: rebuild the context's own ESDF from the occupancy grid a previous alore_esdf_update left on the
+    // device.  The geometry must be the one that map was created with: a different shape with the same cell count
+    // (4096x4096 vs 8192x2048) would silently re-stride the buffers.
     if (!ctx->d_occ || !ctx->d_dist || (size_t)geom->glx * geom->gly != ctx->map_cells)
       return alore_fail(ctx, ALORE_ENOMAP, "no resident occupancy grid of this geometry: call alore_esdf_update first");
+    if (std::memcmp(&ctx->geom, geom, sizeof(*geom)) != 0)
+      return alore_fail(ctx, ALORE_EINVAL, "geometry differs from the resident map's (%dx%d): call alore_esdf_update / alore_esdf_reset first",
+                        ctx->geom.glx, ctx->geom.gly);
     d_occ = ctx->d_occ;
     d_dist_inout = ctx->d_dist;
   } else if (!d_occ || !d_dist_inout) {
     return alore_fail(ctx, ALORE_EINVAL, "pass both device buffers, or neither to use the context's resident map");
   }
-  ctx->geom = *geom;
+  // caller-buffer mode: the caller's geometry describes the caller's buffers only; the context's resident map (and the
+  // geometry the optimizer entry points read) is left untouched
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-  int rc = alore_esdf_run(ctx, d_occ, d_dist_inout, min_x, min_y, max_x, max_y, ref_compat, st, nullptr, nullptr);
+  int rc = alore_esdf_run(ctx, geom, d_occ, d_dist_inout, min_x, min_y, max_x, max_y, ref_compat, st, nullptr, nullptr);
   if (rc == ALORE_OK && resident) ctx->have_map = true;
   return rc;
 }
@@ -251,7 +259,7 @@ int alore_esdf_last_sq(alore_ctx* ctx, int32_t* pos_sq, int32_t* neg_sq) {
   int32_t *dp = nullptr, *dn = nullptr;
   ALORE_CUDA(ctx, cudaMalloc(&dp, n * sizeof(int32_t)));
   if (cudaMalloc(&dn, n * sizeof(int32_t)) != cudaSuccess) { cudaFree(dp); return alore_fail(ctx, ALORE_ENOMEM, "cudaMalloc"); }
-  int rc = alore_esdf_run(ctx, ctx->d_occ, ctx->d_dist, ctx->win[0], ctx->win[1], ctx->win[2], ctx->win[3],
+  int rc = alore_esdf_run(ctx, &ctx->geom, ctx->d_occ, ctx->d_dist, ctx->win[0], ctx->win[1], ctx->win[2], ctx->win[3],
                           ctx->last_ref_compat, ctx->stream, dp, dn);
   if (rc == ALORE_OK) {
     cudaMemcpyAsync(pos_sq, dp, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);

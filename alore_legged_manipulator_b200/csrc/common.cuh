@@ -54,6 +54,7 @@ struct alore_ctx {
   std::vector<int32_t> sched_piece_off;
   std::vector<int32_t> sched_evals;
   // wavefront optimizer: pinned slots + events through which the host polls the survivor count (never per round)
+  int l2_max_persist = -1, l2_max_window = -1;     // per device (set_l2_window)
   int* h_poll = nullptr;
   cudaEvent_t poll_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -76,5 +77,5 @@ inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {
   } while (0)
 
 // esdf.cu
-int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,
+int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,
                    int ref_compat, cudaStream_t st, int32_t* d_pos_sq, int32_t* d_neg_sq);

@@ -26,6 +26,7 @@
 // 8 B/cell out; on cluttered maps the kernels are ALU-issue bound at 0.40 of the 13 B/cell HBM roofline, on maps
 // with large empty / solid regions the O(distance) search dominates.
 #include <cfloat>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -649,17 +650,20 @@ __global__ void esdf_quirk_col(const int16_t* __restrict__ R, int pitch, int NX,
 
 // Runs K1..K2q on `st`.  d_pos_sq/d_neg_sq != NULL: squared-distance dump of the retained row pass of the
 // last update instead of writing distances (parity tests).
-int alore_esdf_run(alore_ctx* ctx, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,
-                   int ref_compat, cudaStream_t st, int32_t* d_pos_sq, int32_t* d_neg_sq) {
+int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x,
+                   int max_y, int ref_compat, cudaStream_t st, int32_t* d_pos_sq, int32_t* d_neg_sq) {
   const int NX = max_x - min_x + 1, NY = max_y - min_y + 1;
-  const alore_map_geom_t& g = ctx->geom;
+  const alore_map_geom_t& g = *geom;
   if (NX <= 0 || NY <= 0 || min_x < 0 || min_y < 0 || max_x >= g.glx || max_y >= g.gly)
     return alore_fail(ctx, ALORE_EINVAL, "esdf window [%d,%d]x[%d,%d] outside the %dx%d grid", min_x, max_x, min_y, max_y, g.glx, g.gly);
   if (NX > 16384 || NY > 16384)
     return alore_fail(ctx, ALORE_EINVAL, "esdf window %dx%d exceeds the int16/int32 exactness limit 16384", NX, NY);
   const bool sq = d_pos_sq != nullptr;
   {
+    // the sqrt table is per device and filled once; guarded because contexts of several devices may be driven by several host threads
+    static std::mutex tbl_mu;
     static bool tbl_ready[64] = {false};
+    std::lock_guard<std::mutex> lk(tbl_mu);
     if (ctx->device < 64 && !tbl_ready[ctx->device]) {
       esdf_fill_sqrt_table<<<SQRT_TBL / 256, 256, 0, st>>>();
       ALORE_CUDA(ctx, cudaStreamSynchronize(st));   // other streams / contexts may use the table next

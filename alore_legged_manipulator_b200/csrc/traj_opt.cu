@@ -352,12 +352,24 @@ struct Launch {
   int* counter = nullptr;
 };
 
-template <typename Kern>
-int prepare_launch(alore_ctx* ctx, const alore_params_t* prm, int Nmax, int B, Kern kern, Launch& L, bool need_history) {
-  if (!ctx->have_map || !ctx->d_dist) return alore_fail(ctx, ALORE_ENOMAP, "no ESDF resident on the device: call alore_esdf_update / alore_esdf_set first");
+int validate_opt_params(alore_ctx* ctx, const alore_params_t* prm) {
   if (prm->sparseResolution < 1 || prm->sparseResolution > 64) return alore_fail(ctx, ALORE_EINVAL, "sparseResolution out of range");
   if (prm->finalSafeDisCheckNum < 1 || prm->finalSafeDisCheckNum > 64) return alore_fail(ctx, ALORE_EINVAL, "finalSafeDisCheckNum out of range");
   if (prm->n_checkpoints < 0 || prm->n_checkpoints > ALORE_MAX_CHECKPOINTS) return alore_fail(ctx, ALORE_EINVAL, "n_checkpoints out of range");
+  // the past-cost ring of lbfgs_optimize (lbfgs.hpp:511) is carved as 64 doubles per candidate
+  for (int past : {prm->lbfgs.past, prm->path_lbfgs.past, prm->normal_past, prm->shot_path_past})
+    if (past < 0 || past > 64) return alore_fail(ctx, ALORE_EINVAL, "lbfgs `past` must be in [0, 64]");
+  if (prm->safeReplanMaxTime < 1) return alore_fail(ctx, ALORE_EINVAL, "safeReplanMaxTime must be >= 1");
+  return ALORE_OK;
+}
+
+template <typename Kern>
+int prepare_launch(alore_ctx* ctx, const alore_params_t* prm, int Nmax, int B, Kern kern, Launch& L, bool need_history) {
+  if (!ctx->have_map || !ctx->d_dist) return alore_fail(ctx, ALORE_ENOMAP, "no ESDF resident on the device: call alore_esdf_update / alore_esdf_set first");
+  {
+    const int vrc = validate_opt_params(ctx, prm);
+    if (vrc) return vrc;
+  }
   ALORE_CUDA(ctx, cudaSetDevice(ctx->device));
   L.kp.P = *prm;
   const alore_map_geom_t& g = ctx->geom;
@@ -401,20 +413,25 @@ int prepare_launch(alore_ctx* ctx, const alore_params_t* prm, int Nmax, int B, K
 // Ask L2 to keep the per-warp evaluation scratch (factors, coefficients, sin/cos, ...) resident while the L-BFGS
 // history — touched once per iteration, ~1 MB per warp — streams through (it would otherwise evict the scratch).
 void set_l2_window(alore_ctx* ctx, cudaStream_t st, void* base, size_t bytes) {
-  static int max_persist = -1, max_window = -1;
-  if (max_persist < 0) {
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-    if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+  if (ctx->l2_max_persist < 0) {                 // limits of THIS context's device
+    cudaDeviceGetAttribute(&ctx->l2_max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&ctx->l2_max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (ctx->l2_max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ctx->l2_max_persist);
   }
-  if (max_persist <= 0 || max_window <= 0) return;
+  if (ctx->l2_max_persist <= 0 || ctx->l2_max_window <= 0) return;
   if (getenv("ALORE_NO_L2_WINDOW")) return;   // tuning knob
   cudaStreamAttrValue v{};
   v.accessPolicyWindow.base_ptr = base;
-  v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
-  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)std::max<size_t>(v.accessPolicyWindow.num_bytes, 1));
+  v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)ctx->l2_max_window);
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_max_persist / (double)std::max<size_t>(v.accessPolicyWindow.num_bytes, 1));
   v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) (void)cudaGetLastError();
+}
+// the caller's stream (e.g. torch's) must not keep our window after the launch that wanted it
+void clear_l2_window(cudaStream_t st) {
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.num_bytes = 0;
   if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) (void)cudaGetLastError();
 }
 
@@ -477,17 +494,6 @@ struct WaveLaunch {
   int grid_solve = 0, grid_pen = 0, grid_step = 0;
   size_t smem_solve = 0, smem_pen = 0, smem_step = 0;
 };
-
-int validate_opt_params(alore_ctx* ctx, const alore_params_t* prm) {
-  if (prm->sparseResolution < 1 || prm->sparseResolution > 64) return alore_fail(ctx, ALORE_EINVAL, "sparseResolution out of range");
-  if (prm->finalSafeDisCheckNum < 1 || prm->finalSafeDisCheckNum > 64) return alore_fail(ctx, ALORE_EINVAL, "finalSafeDisCheckNum out of range");
-  if (prm->n_checkpoints < 0 || prm->n_checkpoints > ALORE_MAX_CHECKPOINTS) return alore_fail(ctx, ALORE_EINVAL, "n_checkpoints out of range");
-  // the past-cost ring of lbfgs_optimize (lbfgs.hpp:511) is carved as 64 doubles per candidate
-  for (int past : {prm->lbfgs.past, prm->path_lbfgs.past, prm->normal_past, prm->shot_path_past})
-    if (past < 0 || past > 64) return alore_fail(ctx, ALORE_EINVAL, "lbfgs `past` must be in [0, 64]");
-  if (prm->safeReplanMaxTime < 1) return alore_fail(ctx, ALORE_EINVAL, "safeReplanMaxTime must be >= 1");
-  return ALORE_OK;
-}
 
 // Carves the per-candidate optimizer state of a batch with `tot` pieces from the context's scratch arena.
 int wave_prepare(alore_ctx* ctx, const alore_params_t* prm, int B, int tot, int Nmax, const int* d_piece_off, const size_t* d_hist_off,
@@ -863,6 +869,7 @@ int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, 
     set_l2_window(ctx, st, L.slabs, (size_t)L.slots * L.kp.L.total * sizeof(double));
     opt_kernel<<<L.slots, 32, L.smem, st>>>(L.kp, bh->bt, bh->res, L.slabs, L.hists, L.counter);
     ctx->launches++;
+    clear_l2_window(st);
     ALORE_CUDA(ctx, cudaGetLastError());
     ALORE_CUDA(ctx, cudaEventRecord(bh->e1, st));
     return ALORE_OK;

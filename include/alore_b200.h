@@ -18,8 +18,11 @@
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a
  * negative ALORE_E* code on failure (never throws across the ABI); alore_last_error() gives
- * the message.  All functions are blocking.  A context is bound to ONE CUDA device and is
- * not re-entrant (the reference runs everything on one ros::spin() thread).
+ * the message.  All functions are blocking unless they take a cuda_stream.  A context is bound to ONE CUDA device and
+ * is not re-entrant (the reference runs everything on one ros::spin() thread): at most ONE operation per context may be
+ * in flight — the *_dev / alore_batch_run entry points that are asynchronous on a caller stream share the context's
+ * scratch (optimizer state, history, work counters), so the caller must order a second call after the first (same
+ * stream, or an event).  Use one context per concurrent stream, or alore_create_multi for several GPUs.
  *
  * Grid layout is the reference's: cell (x, y) lives at index x*GLY + y (y contiguous),
  * sdf_map.cpp:525-527.  Cell states: 0 Unknown, 1 Unoccupied, 2 Occupied (sdf_map.h:98).
@@ -192,7 +195,9 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
 
 /* Same, with occ and dist already in device memory (HBM-resident path used for kernel timing),
  * asynchronous on cuda_stream.  d_occ == NULL and d_dist_inout == NULL: rebuild the context's own
- * resident ESDF from the occupancy grid the last alore_esdf_update left on the device. */
+ * resident ESDF from the occupancy grid the last alore_esdf_update left on the device (rows never uploaded read as
+ * Unknown, the constructor value of SDFmap::gridmap_); geom must then equal the resident map's geometry (ALORE_EINVAL
+ * otherwise).  With caller buffers, geom describes those buffers only and the context's resident map is untouched. */
 int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ,
                           int min_x, int min_y, int max_x, int max_y,
                           double* d_dist_inout, int ref_compat, void* cuda_stream);
