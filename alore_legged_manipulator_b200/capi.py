@@ -220,6 +220,17 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.alore_esdf_last_sq.argtypes = [vp, c_int32_p, c_int32_p]
     lib.alore_esdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.alore_launch_count.argtypes = [vp]
+    lib.alore_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.alore_destroy_multi.argtypes = [vp]
+    lib.alore_destroy_multi.restype = None
+    lib.alore_multi_size.argtypes = [vp]
+    lib.alore_multi_ctx.argtypes = [vp, C.c_int]
+    lib.alore_multi_ctx.restype = vp
+    lib.alore_multi_last_error.argtypes = [vp]
+    lib.alore_multi_last_error.restype = C.c_char_p
+    lib.alore_multi_esdf_update.argtypes = [vp, C.POINTER(MapGeom), c_uint8_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int]
+    lib.alore_multi_opt_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(Candidates), C.POINTER(Results), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_int32), c_int32_p]
     lib.alore_launch_count.restype = C.c_longlong
     if hasattr(lib, "alore_penalty_batch"):
         lib.alore_penalty_batch.argtypes = [vp, C.POINTER(Params), C.c_int, c_int32_p, c_double_p, c_double_p,
@@ -256,6 +267,8 @@ EXPORTED_SYMBOLS = [
     "alore_opt_batch", "alore_batch_upload", "alore_batch_run", "alore_batch_download",
     "alore_batch_device_results", "alore_batch_argmin", "alore_batch_last_kernel_ms", "alore_batch_stats", "alore_batch_free",
     "alore_final_collision_batch", "alore_selftest_division", "alore_debug_force_exact_division", "alore_debug_phase_cycles", "alore_debug_wave_counters", "alore_launch_count",
+    "alore_create_multi", "alore_destroy_multi", "alore_multi_size", "alore_multi_ctx", "alore_multi_last_error",
+    "alore_multi_esdf_update", "alore_multi_opt_batch",
 ]
 
 

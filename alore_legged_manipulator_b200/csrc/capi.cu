@@ -171,10 +171,13 @@ static int ensure_map(alore_ctx* ctx, const alore_map_geom_t* geom, bool force_f
   return ALORE_OK;
 }
 
-int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* occ, int min_x, int min_y, int max_x,
-                      int max_y, double* dist_inout, int ref_compat) {
+}  // extern "C"
+
+// dist_inout == NULL: no host mirror is written (replica devices of alore_multi keep the ESDF in HBM only)
+int alore_esdf_update_impl(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* occ, int min_x, int min_y, int max_x,
+                           int max_y, double* dist_inout, int ref_compat) {
   if (!ctx) return ALORE_EINVAL;
-  if (!occ || !dist_inout) return alore_fail(ctx, ALORE_EINVAL, "null buffer");
+  if (!occ) return alore_fail(ctx, ALORE_EINVAL, "null buffer");
   int rc = ensure_map(ctx, geom);
   if (rc) return rc;
   const int NX = max_x - min_x + 1, NY = max_y - min_y + 1;
@@ -191,7 +194,7 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
   ALORE_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
   // D2H: exactly the rectangle the reference writes.
   const int wx = ref_compat ? NX - 1 : NX, wy = ref_compat ? NY - 1 : NY;
-  if (wx > 0 && wy > 0) {
+  if (dist_inout && wx > 0 && wy > 0) {
     const size_t o = (size_t)min_x * gly + min_y;
     ALORE_CUDA(ctx, cudaMemcpy2DAsync(dist_inout + o, gly * sizeof(double), ctx->d_dist + o, gly * sizeof(double),
                                       (size_t)wy * sizeof(double), wx, cudaMemcpyDeviceToHost, st));
@@ -200,6 +203,15 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
   ALORE_CUDA(ctx, cudaEventElapsedTime(&ctx->esdf_kernel_ms, ctx->ev0, ctx->ev1));
   ctx->have_map = true;
   return ALORE_OK;
+}
+
+extern "C" {
+
+int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* occ, int min_x, int min_y, int max_x,
+                      int max_y, double* dist_inout, int ref_compat) {
+  if (!ctx) return ALORE_EINVAL;
+  if (!dist_inout) return alore_fail(ctx, ALORE_EINVAL, "null buffer");
+  return alore_esdf_update_impl(ctx, geom, occ, min_x, min_y, max_x, max_y, dist_inout, ref_compat);
 }
 
 int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ, int min_x, int min_y,

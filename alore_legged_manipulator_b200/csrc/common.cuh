@@ -79,3 +79,6 @@ inline int alore_fail(alore_ctx* ctx, int code, const char* fmt, ...) {
 // esdf.cu
 int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ, double* d_dist, int min_x, int min_y, int max_x, int max_y,
                    int ref_compat, cudaStream_t st, int32_t* d_pos_sq, int32_t* d_neg_sq);
+// capi.cu: alore_esdf_update with an optional host mirror (dist_inout == NULL: keep the result in HBM only)
+int alore_esdf_update_impl(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* occ, int min_x, int min_y, int max_x,
+                           int max_y, double* dist_inout, int ref_compat);

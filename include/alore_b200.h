@@ -290,6 +290,25 @@ int alore_final_collision_batch(alore_ctx* ctx, const alore_params_t* prm, int B
                                 const double* piece_T, const double* start_xy,
                                 int32_t* collided, double* min_dist);
 
+/* ---- several GPUs of one box behind one object (SURVEY.md section 8b ownership row, 8e) -------------------------------
+ * The reference's caller is one C++ process (PlanManager, plan_manager.hpp:120-123, :662-670); alore_multi gives it the
+ * multi-GPU path without a launcher: one host thread per device inside the library, the ESDF replicated (every device
+ * rebuilds it from the 1 B/cell occupancy grid), the candidate array cut into contiguous blocks of (nearly) equal
+ * piece counts, and ONE exchange: an all-gather over NCCL of (best cost, global index), 16 bytes per device.  Results
+ * are written into the caller's arrays exactly where alore_opt_batch would write them (a candidate's result does not
+ * depend on which device or block it ran in).  best_idx = -1 when no candidate succeeded.  block_offsets [n+1] (may be
+ * NULL) receives the block boundaries.  NCCL is loaded at run time (dlopen) and only when n > 1. */
+typedef struct alore_multi alore_multi;
+int alore_create_multi(const int* devices, int n, alore_multi** out);
+void alore_destroy_multi(alore_multi* m);
+int alore_multi_size(const alore_multi* m);
+alore_ctx* alore_multi_ctx(alore_multi* m, int i);           /* the per-device context (owned by m) */
+const char* alore_multi_last_error(const alore_multi* m);
+int alore_multi_esdf_update(alore_multi* m, const alore_map_geom_t* geom, const uint8_t* occ,
+                            int min_x, int min_y, int max_x, int max_y, double* dist_inout, int ref_compat);
+int alore_multi_opt_batch(alore_multi* m, const alore_params_t* prm, const alore_candidates_t* cands,
+                          alore_results_t* out, double* best_cost, int32_t* best_idx, int32_t* block_offsets);
+
 /* Self-test of the kernels' split IEEE division (csrc/traj_opt.cuh: rcp_refine + div_rcp, used on the dependent
  * chains of the banded LU / triangular sweeps that replace minco.hpp:99-197) against the compiler's a / b on
  * n_pairs generated operand pairs (all exponents, specials, solver-range magnitudes).  *mismatches = differing bits. */
