@@ -231,8 +231,21 @@ int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const ui
                         ctx->geom.glx, ctx->geom.gly);
     d_occ = ctx->d_occ;
     d_dist_inout = ctx->d_dist;
+  } else if (d_occ && !d_dist_inout) {
+    // resident update from a DEVICE occupancy grid: the window's rows are copied into the context's grid (device to
+    // device, what alore_esdf_update does from the host) and the resident ESDF is rebuilt
+    if (!ctx->d_occ || !ctx->d_dist || (size_t)geom->glx * geom->gly != ctx->map_cells || std::memcmp(&ctx->geom, geom, sizeof(*geom)) != 0)
+      return alore_fail(ctx, ALORE_ENOMAP, "no resident map of this geometry: call alore_esdf_update / alore_esdf_reset first");
+    if (min_x < 0 || max_x >= geom->glx || max_x < min_x) return alore_fail(ctx, ALORE_EINVAL, "esdf window outside the grid");
+    cudaStream_t st2 = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const size_t gly = geom->gly;
+    ALORE_CUDA(ctx, cudaMemcpyAsync(ctx->d_occ + (size_t)min_x * gly, d_occ + (size_t)min_x * gly, (size_t)(max_x - min_x + 1) * gly,
+                                    cudaMemcpyDeviceToDevice, st2));
+    int rc2 = alore_esdf_run(ctx, geom, ctx->d_occ, ctx->d_dist, min_x, min_y, max_x, max_y, ref_compat, st2, nullptr, nullptr);
+    if (rc2 == ALORE_OK) ctx->have_map = true;
+    return rc2;
   } else if (!d_occ || !d_dist_inout) {
-    return alore_fail(ctx, ALORE_EINVAL, "pass both device buffers, or neither to use the context's resident map");
+    return alore_fail(ctx, ALORE_EINVAL, "pass both device buffers, the occupancy alone, or neither");
   }
   // caller-buffer mode: the caller's geometry describes the caller's buffers only; the context's resident map (and the
   // geometry the optimizer entry points read) is left untouched

@@ -476,6 +476,7 @@ struct alore_batch {
   size_t* d_hist_off = nullptr;     // [B] offset (doubles) of each candidate's L-BFGS history ring, for mem_size = hist_m
   int hist_m = 0;
   size_t hist_doubles = 0;
+  bool predicted = false;           // d_order currently holds a predicted (not piece-count) order
   int rounds = 0;                   // rounds of the last run (one round = one cost evaluation of every unfinished candidate)
   bool pooled = false;              // device arrays carved from ctx->batch_pool
   char* pool_cur = nullptr;
@@ -788,9 +789,7 @@ static int batch_upload_impl(alore_ctx* ctx, const alore_candidates_t* c, alore_
   cudaStream_t st = ctx->stream;
   bh->piece_off.assign(c->piece_off, c->piece_off + B + 1);
   std::vector<int> order;
-  std::vector<int32_t> pred;
-  const bool known = predicted_evals(ctx, bh->piece_off, pred);
-  lpt_order(bh->piece_off, known ? pred.data() : nullptr, order);
+  lpt_order(bh->piece_off, nullptr, order);            // piece-count order; alore_batch_run refines it from the previous tick
   int* d_po; int* d_order; double *d_ip, *d_T, *d_pos, *d_ss, *d_fs, *d_sx, *d_fx; unsigned char* d_cut;
   if (use_arena && !ctx->batch_pool_busy) {   // one-shot calls carve every device array from the context's arena
     const size_t need = 8 * (48 * (size_t)B + 40 * (size_t)tot) + 64 * 1024;
@@ -852,16 +851,34 @@ int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, 
     Launch L;
     int rc = prepare_launch(ctx, prm, bh->Nmax, bh->B, opt_kernel, L, true);
     if (rc) return rc;
-    if (bh->runs > 0) {   // a resident batch that is optimised again: longest predicted work (pieces x previous evaluations) first
-      std::vector<int32_t> ev(bh->B);
-      ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), bh->res.evals, bh->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    // Hand-out order of the work queue: longest predicted work first.  Prediction = pieces x cost evaluations the
+    // candidate at the same index needed on the PREVIOUS tick (this handle's last run, or the last run of any handle
+    // on this context with the same structure: a replanning planner re-optimises mostly the same legs), else pieces.
+    if (ctx->last_batch) {                            // collect the previous tick's evaluation counts (it has finished: same-context ordering)
+      alore_batch* pb = static_cast<alore_batch*>(ctx->last_batch);
+      ALORE_CUDA(ctx, cudaEventSynchronize(pb->e1));   // that run may have been enqueued on another stream
+      std::vector<int32_t> ev(pb->B);
+      ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), pb->res.evals, pb->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       ALORE_CUDA(ctx, cudaStreamSynchronize(st));
-      std::vector<int> order;
-      lpt_order(bh->piece_off, ev.data(), order);
-      ALORE_CUDA(ctx, cudaMemcpyAsync(bh->d_order, order.data(), bh->B * sizeof(int), cudaMemcpyHostToDevice, st));
-      ALORE_CUDA(ctx, cudaStreamSynchronize(st));
-      ctx->sched_piece_off = bh->piece_off;
-      ctx->sched_evals = ev;
+      ctx->sched_piece_off = pb->piece_off;
+      ctx->sched_evals.swap(ev);
+      ctx->last_batch = nullptr;
+    }
+    {
+      std::vector<int32_t> pred;
+      if (!getenv("ALORE_NO_SCHED_PREDICTION") && predicted_evals(ctx, bh->piece_off, pred)) {
+        std::vector<int> order;
+        lpt_order(bh->piece_off, pred.data(), order);
+        ALORE_CUDA(ctx, cudaMemcpyAsync(bh->d_order, order.data(), bh->B * sizeof(int), cudaMemcpyHostToDevice, st));
+        ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+        bh->predicted = true;
+      } else if (bh->predicted) {                     // back to the piece-count order
+        std::vector<int> order;
+        lpt_order(bh->piece_off, nullptr, order);
+        ALORE_CUDA(ctx, cudaMemcpyAsync(bh->d_order, order.data(), bh->B * sizeof(int), cudaMemcpyHostToDevice, st));
+        ALORE_CUDA(ctx, cudaStreamSynchronize(st));
+        bh->predicted = false;
+      }
     }
     bh->runs++;
     ALORE_CUDA(ctx, cudaMemsetAsync(L.counter, 0, sizeof(int), st));
@@ -872,6 +889,7 @@ int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, 
     clear_l2_window(st);
     ALORE_CUDA(ctx, cudaGetLastError());
     ALORE_CUDA(ctx, cudaEventRecord(bh->e1, st));
+    ctx->last_batch = bh;
     return ALORE_OK;
   }
   bh->runs++;
@@ -890,13 +908,7 @@ int alore_batch_download(alore_ctx* ctx, alore_batch* bh, alore_results_t* out) 
   DN(out->evals, r.evals, B) DN(out->cost, r.cost, B) DN(out->inner_pts, r.inner_pts, 2 * (size_t)(tot - B))
   DN(out->tail_s, r.tail_s, B) DN(out->piece_T, r.piece_T, tot) DN(out->coeffs, r.coeffs, 12 * (size_t)tot)
 #undef DN
-  {
-    std::vector<int32_t> ev(B);
-    ALORE_CUDA(ctx, cudaMemcpyAsync(ev.data(), r.evals, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    ALORE_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->sched_piece_off = bh->piece_off;
-    ctx->sched_evals.swap(ev);
-  }
+  ALORE_CUDA(ctx, cudaStreamSynchronize(st));
   cudaEventElapsedTime(&bh->kernel_ms, bh->e0, bh->e1);
   (void)cudaGetLastError();
   return ALORE_OK;
@@ -953,6 +965,16 @@ void alore_batch_free(alore_batch* bh) {
   if (!bh) return;
   if (bh->ctx) cudaSetDevice(bh->ctx->device);
   cudaDeviceSynchronize();
+  if (bh->ctx && bh->ctx->last_batch == bh) {        // keep this tick's evaluation counts for the next tick's schedule
+    std::vector<int32_t> ev(bh->B);
+    if (cudaMemcpy(ev.data(), bh->res.evals, bh->B * sizeof(int32_t), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      bh->ctx->sched_piece_off = bh->piece_off;
+      bh->ctx->sched_evals.swap(ev);
+    } else {
+      (void)cudaGetLastError();
+    }
+    bh->ctx->last_batch = nullptr;
+  }
   for (void* p : bh->allocs) cudaFree(p);
   if (bh->pooled && bh->ctx) bh->ctx->batch_pool_busy = false;
   if (bh->e0) cudaEventDestroy(bh->e0);

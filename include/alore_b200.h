@@ -197,7 +197,9 @@ int alore_esdf_update(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_
  * asynchronous on cuda_stream.  d_occ == NULL and d_dist_inout == NULL: rebuild the context's own
  * resident ESDF from the occupancy grid the last alore_esdf_update left on the device (rows never uploaded read as
  * Unknown, the constructor value of SDFmap::gridmap_); geom must then equal the resident map's geometry (ALORE_EINVAL
- * otherwise).  With caller buffers, geom describes those buffers only and the context's resident map is untouched. */
+ * otherwise).  d_occ != NULL and d_dist_inout == NULL: the window's rows of the DEVICE grid d_occ are first copied into
+ * the context's resident grid (what alore_esdf_update does from the host), then the resident ESDF is rebuilt.  With both
+ * caller buffers, geom describes those buffers only and the context's resident map is untouched. */
 int alore_esdf_update_dev(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* d_occ,
                           int min_x, int min_y, int max_x, int max_y,
                           double* d_dist_inout, int ref_compat, void* cuda_stream);
@@ -258,9 +260,10 @@ int alore_cost_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_cand
 /* ---- full optimisation, batched: B x MSPlanner::minco_plan (optimizer.cpp:169-220) ---- */
 /* HOST pointers in cands/out.  B = 1 reproduces one minco_plan call.  Blocking.  The device copies of the batch are
  * carved from an arena the context keeps (no cudaMalloc/cudaFree per call), and the hand-out order of the candidates
- * to the resident warps uses the evaluation counts of the previous call with a similar batch (same B, same piece
- * count at the same index for >= 3/4 of the candidates): longest predicted work first.  Neither affects a result:
- * every candidate is optimised independently and deterministically. */
+ * to the resident warps uses the evaluation counts of the previous optimisation on this context with a similar batch
+ * (same B, same piece count at the same index for >= 3/4 of the candidates; a replanning planner re-optimises mostly
+ * the same legs every tick): longest predicted work first, piece counts alone otherwise (env ALORE_NO_SCHED_PREDICTION=1
+ * forces the latter).  Neither affects a result: every candidate is optimised independently and deterministically. */
 int alore_opt_batch(alore_ctx* ctx, const alore_params_t* prm, const alore_candidates_t* cands,
                     alore_results_t* out);
 

@@ -388,6 +388,40 @@ void orc_smoothed_l1(double eps, double x, double* f, double* df) {   // optimiz
   pl.positiveSmoothedL1(x, *f, *df);
 }
 
+// The reference's yaml defaults (back_end/config/global_planning3ms.yaml, plan_tester/config/car3ms.yaml,
+// plan_tester/launch/planner_sim.launch:41-46; lbfgs.hpp:76-128), stated here a second time so that the CPU arm of
+// bench.py needs nothing of the product library; tests/test_capi_cpu.py asserts the two agree byte for byte.
+static void orc_lbfgs_defaults(alore_lbfgs_params_t* l) {
+  l->mem_size = 8; l->past = 3; l->max_iterations = 0; l->max_linesearch = 64;
+  l->g_epsilon = 1.0e-5; l->delta = 1.0e-6; l->min_step = 1.0e-20; l->max_step = 1.0e+20;
+  l->f_dec_coeff = 1.0e-4; l->s_curv_coeff = 0.9; l->cautious_factor = 1.0e-6; l->machine_prec = 1.0e-16;
+}
+void orc_params_default(alore_params_t* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->max_vel = 3.0; p->min_vel = -3.0; p->max_acc = 2.0; p->max_omega = 3.0; p->max_domega = 4.0;
+  p->max_centripetal_acc = 50.0; p->if_directly_constrain_v_omega = 0; p->if_standard_diff = 1;
+  p->ICR[0] = 0.3; p->ICR[1] = -0.3; p->ICR[2] = 0.2;
+  p->mean_time_lowBound = 0.5; p->mean_time_uppBound = 2.0;
+  p->smoothEps = 0.01; p->safeDis = 0.6; p->finalMinSafeDis = 0.10; p->finalSafeDisCheckNum = 16; p->safeReplanMaxTime = 3;
+  p->pw_time = 50; p->pw_acc = 300; p->pw_domega = 300; p->pw_collision = 500000; p->pw_moment = 300; p->pw_mean_time = 300; p->pw_cen_acc = 300;
+  p->ppw_time = 20; p->ppw_bigpath_sdf = 200000; p->ppw_mean_time = 100; p->ppw_moment = 1000; p->ppw_acc = 100; p->ppw_domega = 100;
+  p->energyWeights[0] = 0.33; p->energyWeights[1] = 1.0;
+  for (int i = 0; i < 2; i++) {
+    p->EqualLambda[i] = 0; p->EqualRho[i] = 10000.0; p->EqualRhoMax[i] = 1.0e10; p->EqualGamma[i] = 9.0;
+    p->CutEqualLambda[i] = 0; p->CutEqualRho[i] = 1000.0; p->CutEqualRhoMax[i] = 1.0e10; p->CutEqualGamma[i] = 5.0;
+  }
+  p->EqualTolerance[0] = 0.01; p->EqualTolerance[1] = 0.0; p->CutEqualTolerance[0] = 0.5; p->CutEqualTolerance[1] = 0.0;
+  orc_lbfgs_defaults(&p->path_lbfgs);
+  p->path_lbfgs.mem_size = 256; p->path_lbfgs.past = 2; p->path_lbfgs.g_epsilon = 0.0; p->path_lbfgs.min_step = 0.0;
+  p->path_lbfgs.delta = 5.0e-2; p->path_lbfgs.max_iterations = 8000;
+  p->normal_past = 2; p->shot_path_past = 8; p->shot_path_horizon = 0.5;
+  orc_lbfgs_defaults(&p->lbfgs);
+  p->lbfgs.mem_size = 256; p->lbfgs.past = 3; p->lbfgs.g_epsilon = 0.0; p->lbfgs.min_step = 1.0e-32; p->lbfgs.delta = 5.0e-4;
+  p->lbfgs.max_iterations = 8000;
+  p->sparseResolution = 8; p->n_checkpoints = 1; p->check_point[0][0] = 0.0; p->check_point[0][1] = 0.0;
+  p->alm_max_outer = 0;
+}
+
 void orc_set_exact_chain_weights(int on) { orc::g_exact_chain_weights = on != 0; }
 
 void orc_set_trig_portable(int on) { orc::g_trig_portable = on != 0; }

@@ -56,11 +56,21 @@ def load():
     lib.orc_frontend_make.argtypes = [C.c_int, dp, dp, dp, dp, dp] + [C.c_double] * 6 + [C.c_int, C.c_int, dp, dp, dp,
                                                                                        dp, dp, dp, u8p]
     lib.orc_hardware_threads.restype = C.c_int
+    lib.orc_params_default.argtypes = [P]
+    lib.orc_params_default.restype = None
     _lib = lib
     return lib
 
 
 # ---- convenience wrappers ----------------------------------------------------------------
+
+def default_params() -> capi.Params:
+    """The reference's yaml defaults WITHOUT touching the product library (the oracle states them a second time)."""
+    p = capi.Params()
+    load().orc_params_default(C.byref(p))
+    return p
+
+
 
 def esdf_update(geom: capi.MapGeom, occ: np.ndarray, mn, mx, dist: np.ndarray, want_sq=False):
     lib = load()

@@ -81,3 +81,11 @@ def test_null_and_bad_arguments_return_error_codes():
     assert lib.alore_opt_batch(None, None, None, None) == -1
     assert lib.alore_batch_run(None, None, None, None) == -1
     assert lib.alore_launch_count(None) == 0
+
+
+def test_oracle_states_the_same_defaults():
+    """bench.py's CPU arm takes its parameters from the oracle (it must not load the product library)."""
+    import ctypes as C
+    import oracle_lib
+    a, b = capi.default_params(), oracle_lib.default_params()
+    assert bytes(C.string_at(C.addressof(a), C.sizeof(a))) == bytes(C.string_at(C.addressof(b), C.sizeof(b)))
