@@ -26,6 +26,7 @@
 // 8 B/cell out; on cluttered maps the kernels are ALU-issue bound at 0.40 of the 13 B/cell HBM roofline, on maps
 // with large empty / solid regions the O(distance) search dominates.
 #include <cfloat>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -616,6 +617,119 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   }
 }
 
+// K2dc: exact column pass whose cost does not depend on the map — divide and conquer on the MONOTONE OWNER.
+//
+// For one column and one kind, val(X) = min_x' (X-x')^2 + g(x')^2 is the lower envelope of equal-curvature parabolas
+// (what fillESDF builds with its stack, sdf_map.cpp:682-715), so the minimising row own(X) is non-decreasing in X.
+// Resolve X = 0 first, then level by level the mid-points X = (2i+1)h, h = n/2, n/4, .., 1: the candidates of a query
+// are only the rows in [own(X-h), own(X+h)], scanned outwards from the row nearest to X with the exact cut-off
+// (X-x')^2 >= best.  Near seeds (cluttered maps) the cut-off ends a scan after a few probes; far from seeds (large
+// empty or solid regions, where an expanding search pays O(distance) per cell) the neighbours' owners are close
+// together, so the interval is a few rows wide.  Total work is O(n log n) per column in the worst case, O(n) typically,
+// and never depends on how far the nearest seed is.  Ties may pick any minimiser: a tie at X between rows p < q means p
+// wins left of X and q right of it, so either owner bounds the sub-ranges correctly.  Integer arithmetic throughout.
+// One CTA owns a strip of DC columns x all NX rows: the row distances (int16) and the two owner arrays (int16 per kind)
+// live in shared memory (6 bytes per cell), levels are separated by CTA barriers, low levels (few, long scans) use up
+// to 32 lanes per query.  Both kinds are resolved at every position (the owners of one kind bound that kind's
+// sub-queries); a cell's output is the value of ITS OWN kind, as in K2.
+template <bool SQ>
+__global__ void __launch_bounds__(1024)
+esdf_col_dc(const int16_t* __restrict__ R, int pitch, int NX, int NY, int lgDC, int n_pow2, double* __restrict__ dist, int gly, int min_x,
+            int min_y, double gi, int ref_compat, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  extern __shared__ __align__(16) int16_t dc_smem[];
+  const int DC = 1 << lgDC;
+  int16_t* S = dc_smem;                        // [NX][DC]   row distances
+  int16_t* OWN = dc_smem + NX * DC;            // [2][NX][DC] owner row per kind
+  const int Y0 = blockIdx.x << lgDC;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  // strip load: one 2*DC-byte vector per row (the pitch is a multiple of 128 cells, Y0 of DC: always aligned, never past the pitch)
+  if (lgDC == 4) {
+    for (int x = tid; x < 2 * NX; x += nthr)
+      reinterpret_cast<uint4*>(S)[x] = *reinterpret_cast<const uint4*>(R + (size_t)(x >> 1) * pitch + Y0 + 8 * (x & 1));
+  } else if (lgDC == 3) {
+    for (int x = tid; x < NX; x += nthr) reinterpret_cast<uint4*>(S)[x] = *reinterpret_cast<const uint4*>(R + (size_t)x * pitch + Y0);
+  } else if (lgDC == 2) {
+    for (int x = tid; x < NX; x += nthr) reinterpret_cast<uint2*>(S)[x] = *reinterpret_cast<const uint2*>(R + (size_t)x * pitch + Y0);
+  } else {
+    for (int e = tid; e < NX * DC; e += nthr) S[e] = R[(size_t)(e >> lgDC) * pitch + Y0 + (e & (DC - 1))];
+  }
+  __syncthreads();
+  // columns past NY inside the pitch hold K1's padding; they are resolved like any other and never written out
+  const int lgQ0 = lgDC + 1;                                  // queries per position: DC columns x 2 kinds
+  int lvl = -1, h = n_pow2;
+  for (;;) {
+    const int lgpos = lvl < 0 ? 0 : lvl;                      // 2^lvl positions (2i+1)h at level lvl
+    const int lgQ = lgpos + lgQ0;
+    int lgG = 5;
+    while (lgG > 0 && lgQ + lgG > 10) lgG--;                  // G lanes per query while Q * G <= 1024 threads
+    const int G = 1 << lgG;
+    const int total = 1 << (lgQ + lgG);
+    for (int base = 0; base < total; base += nthr) {
+      const int slot = base + tid;
+      const int q = slot >> lgG, gl = slot & (G - 1);
+      const int c = q & (DC - 1), k = (q >> lgDC) & 1, i = q >> lgQ0;
+      const int X = lvl < 0 ? 0 : (2 * i + 1) * h;
+      const bool live = slot < total && X < NX;
+      int best = 0x7fffffff, arg = 0;
+      if (live) {
+        const int16_t* own = OWN + k * NX * DC + c;
+        const int olo = lvl < 0 ? 0 : own[(X - h) << lgDC];
+        const int ohi = (lvl >= 0 && X + h < NX) ? own[(X + h) << lgDC] : NX - 1;
+        const int16_t* col = S + c;
+        const int c0 = min(max(X, olo), ohi);
+        arg = c0;
+        if (gl == 0) {
+          const int r = col[c0 << lgDC];
+          const int g = k ? max(-r, 0) : max(r, 0);
+          const int d = X - c0;
+          best = d * d + g * g;
+        }
+        // downwards from c0-1, upwards from c0+1, lane gl takes every G-th row; exact cut-off per direction
+        for (int xp = c0 - 1 - gl; xp >= olo; xp -= G) {
+          const int d = X - xp;
+          if (d * d >= best) break;
+          const int r = col[xp << lgDC];
+          const int g = k ? max(-r, 0) : max(r, 0);
+          const int v = d * d + g * g;
+          if (v < best) { best = v; arg = xp; }
+        }
+        for (int xp = c0 + 1 + gl; xp <= ohi; xp += G) {
+          const int d = xp - X;
+          if (d * d >= best) break;
+          const int r = col[xp << lgDC];
+          const int g = k ? max(-r, 0) : max(r, 0);
+          const int v = d * d + g * g;
+          if (v < best) { best = v; arg = xp; }
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) {                  // min over the group (value, then row); every lane of the warp takes part
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o), oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if (live && gl == 0) {
+        OWN[((k * NX + X) << lgDC) + c] = (int16_t)arg;
+        const int y = Y0 + c;
+        const bool neg = S[(X << lgDC) + c] < 0;
+        if (y < NY && (int)neg == k) {                         // the cell's own kind is its output
+          if (SQ) {
+            const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
+            pos_sq[(size_t)X * NY + y] = neg ? 0 : v;
+            neg_sq[(size_t)X * NY + y] = neg ? v : 0;
+          } else {
+            // the reference never writes the window's last row / column; column 0, rows >= 1, is esdf_quirk_col's
+            const bool skip = ref_compat && (X == NX - 1 || y == NY - 1 || (y == 0 && X >= 1));
+            if (!skip) dist[(size_t)(X + min_x) * gly + y + min_y] = esdf_value(best, neg, gi);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (lvl < 0) { lvl = 0; h = n_pow2 >> 1; }
+    else { lvl++; h >>= 1; }
+    if (h < 1) break;
+  }
+}
+
 // K2q: the reference's aliased column (ref_compat).  Window-local column 0, rows X = 1..NX-1, is the 1-D
 // transform over the virtual column W(j), j in [1, NX]:  W(j) = R(j, 0) for j <= NX-1, W(NX) = R(NX-1, NY-1),
 // evaluated at j = X  (sdf_map.cpp:639-650: index x*update_Y_SIZE + y with y == update_Y_SIZE aliases row x+1).
@@ -720,7 +834,23 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
   const dim3 grid((NY + TY - 1) / TY, (NX + TX - 1) / TX);
   const bool quirk = ref_compat && NX >= 2 && NY >= 2;
   if (ref_compat && !quirk && !sq) return ALORE_OK;  // update_X_SIZE or update_Y_SIZE == 0: the reference writes nothing
+  // ---- column pass: divide and conquer on the monotone owner (K2dc), strips of DC columns resident in shared memory
+  int n_pow2 = 1;
+  while (n_pow2 < NX) n_pow2 <<= 1;
+  int DC = 16, lgDC = 4;
+  while (DC > 1 && (size_t)NX * DC * 6 > 200 * 1024) { DC >>= 1; lgDC--; }
+  const bool use_dc = getenv("ALORE_ESDF_DC") != nullptr && (size_t)NX * DC * 6 <= 200 * 1024;
+  const size_t dc_smem = (size_t)NX * DC * 6;
+  const int dc_grid = (NY + DC - 1) / DC;
+  if (use_dc) {
+    ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_col_dc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem));
+    ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_col_dc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem));
+  }
   if (sq) {
+    if (use_dc)
+      esdf_col_dc<true><<<dc_grid, 1024, dc_smem, st>>>(ctx->d_row, pitch, NX, NY, lgDC, n_pow2, d_dist, g.gly, min_x, min_y, g.grid_interval,
+                                                        ref_compat, d_pos_sq, d_neg_sq);
+    else
     esdf_col_pass<true><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
                                               g.grid_interval, ref_compat, d_pos_sq, d_neg_sq);
     ctx->launches++;
@@ -739,6 +869,10 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
       ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
       ctx->launches++;
     }
+    if (use_dc)
+      esdf_col_dc<false><<<dc_grid, 1024, dc_smem, st>>>(ctx->d_row, pitch, NX, NY, lgDC, n_pow2, d_dist, g.gly, min_x, min_y, g.grid_interval,
+                                                         ref_compat, nullptr, nullptr);
+    else
     esdf_col_pass<false><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
                                                g.grid_interval, ref_compat, nullptr, nullptr);
     ctx->launches++;

@@ -1059,25 +1059,40 @@ static int penalty_launch(alore_ctx* ctx, const alore_params_t* prm, int B, int 
   kp.map = MapDev{ctx->d_dist, g.glx, g.gly, g.x_lower, g.y_lower, g.x_upper, g.y_upper, g.grid_interval, g.inv_grid_interval};
   kp.L.init(Nmax, prm->sparseResolution, prm->finalSafeDisCheckNum, prm->n_checkpoints);
   kp.Nmax = Nmax; kp.npadmax = (3 * Nmax) & ~1; kp.mcap = 1;
-  const size_t smem = wave::pen_smem_doubles(Nmax) * sizeof(double);
+  // threads per trajectory x resident CTAs per SM x placement of the per-sample intermediates (tuning knob
+  // ALORE_PEN_SHAPE; default chosen by measurement on configs[2]: 64 threads, 6 CTAs per SM, intermediates in the L2-resident
+  // per-CTA slab — 0.65 ms; 128 threads 0.84, one warp 0.81, shared-memory intermediates 0.77 (8 warps per SM), more CTAs 0.69+)
+  int shape = 64;
+  if (const char* e = getenv("ALORE_PEN_SHAPE")) shape = atoi(e);
+  const size_t smem_on = wave::pen_smem_doubles_onchip(Nmax, prm->sparseResolution) * sizeof(double);
+  const bool onchip = (shape == 641 || shape == 1281) && smem_on <= 200 * 1024;   // measured slower (0.77 vs 0.65 ms at configs[2]): opt-in
+  const size_t smem = onchip ? smem_on : wave::pen_smem_doubles(Nmax) * sizeof(double);
   if (smem > 200 * 1024) return alore_fail(ctx, ALORE_EINVAL, "trajectory with %d pieces exceeds the shared-memory budget", Nmax);
-  ALORE_CUDA(ctx, cudaFuncSetAttribute(wave::penalty_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  ALORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wave::penalty_cta_kernel, wave::PEN_NT, smem));
-  if (occ < 1) return alore_fail(ctx, ALORE_EINVAL, "kernel does not fit on an SM");
-  const int grid = std::max(1, std::min(B, occ * ctx->sm_count));
-  const size_t need = (size_t)grid * kp.L.total * sizeof(double);
-  if (need > ctx->opt_scratch_bytes) {
-    if (ctx->opt_scratch) { cudaDeviceSynchronize(); cudaFree(ctx->opt_scratch); }
-    ctx->opt_scratch = nullptr; ctx->opt_scratch_bytes = 0;
-    ALORE_CUDA(ctx, cudaMalloc(&ctx->opt_scratch, need));
-    ctx->opt_scratch_bytes = need;
-  }
-  wave::penalty_cta_kernel<<<grid, wave::PEN_NT, smem, st>>>(kp, B, d_piece_off, d_coeffs, d_piece_T, d_start_xy, d_final_xy, d_cost,
-                                                             d_gradC, d_gradT, d_xy_err, reinterpret_cast<double*>(ctx->opt_scratch));
-  ctx->launches++;
-  ALORE_CUDA(ctx, cudaGetLastError());
-  return ALORE_OK;
+  auto launch = [&](auto kern, int NT) -> int {
+    ALORE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    ALORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return alore_fail(ctx, ALORE_EINVAL, "kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(B, occ * ctx->sm_count));
+    const size_t need = (size_t)grid * kp.L.total * sizeof(double);
+    if (need > ctx->opt_scratch_bytes) {
+      if (ctx->opt_scratch) { cudaDeviceSynchronize(); cudaFree(ctx->opt_scratch); }
+      ctx->opt_scratch = nullptr; ctx->opt_scratch_bytes = 0;
+      ALORE_CUDA(ctx, cudaMalloc(&ctx->opt_scratch, need));
+      ctx->opt_scratch_bytes = need;
+    }
+    kern<<<grid, NT, smem, st>>>(kp, B, d_piece_off, d_coeffs, d_piece_T, d_start_xy, d_final_xy, d_cost, d_gradC, d_gradT, d_xy_err,
+                                 reinterpret_cast<double*>(ctx->opt_scratch));
+    ctx->launches++;
+    ALORE_CUDA(ctx, cudaGetLastError());
+    return ALORE_OK;
+  };
+  if (shape == 32) return launch(wave::penalty_cta_kernel<32, 16, false>, 32);
+  if (shape == 128) return launch(wave::penalty_cta_kernel<128, 3, false>, 128);
+  if (shape == 640) return launch(wave::penalty_cta_kernel<64, 6, false>, 64);
+  if (shape == 1281 && onchip) return launch(wave::penalty_cta_kernel<128, 2, true>, 128);
+  if (onchip) return launch(wave::penalty_cta_kernel<64, 4, true>, 64);
+  return launch(wave::penalty_cta_kernel<64, 6, false>, 64);
 }
 
 int alore_penalty_batch_dev(alore_ctx* ctx, const alore_params_t* prm, int B, int max_pieces, const int32_t* d_piece_off,

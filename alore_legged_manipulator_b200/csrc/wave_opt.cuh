@@ -590,15 +590,32 @@ __host__ __device__ inline size_t pen_smem_doubles(int Nmax) {
   // T1[N] gT[N] pXY[2(N+1)] bcast[4] | stg[1024] (cell-prefix chunks 2 x 256, cost-term packing 512)
   return (size_t)Nmax + Nmax + 2 * (Nmax + 1) + 4 + 2 + 1024;
 }
+// + the per-sample intermediates on chip: cs[2S] | ax[S+64] ay[S+64] (dead after the cell integrals; g2p[2N(K+1)] takes
+// their place from pass B on) | cellP[2NK]
+__host__ __device__ inline size_t pen_smem_doubles_onchip(int Nmax, int K) {
+  const size_t S = (size_t)Nmax * (2 * K + 1);
+  const size_t axy = 2 * (S + 64), g2 = 2 * (size_t)Nmax * (K + 1);
+  return pen_smem_doubles(Nmax) + 2 * S + (axy > g2 ? axy : g2) + 2 * (size_t)Nmax * K + 8;
+}
+template <bool SH>
 __device__ __forceinline__ void pen_carve(Warp& w, const PenLayout& L, double* smem, double* slab, int Nmax, int N, int K) {
   w.lane = threadIdx.x;
   w.N = N; w.n = 3 * N - 1; w.npad = (3 * N) & ~1; w.n6 = 6 * N; w.K = K; w.S1 = 2 * K + 1;
   double* s = smem;
   w.T1 = s; s += Nmax; w.gT = s; s += Nmax; w.pXY = s; s += 2 * (Nmax + 1); w.sumT = s; s += 4;
   s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s) + 15) & ~uintptr_t(15));
-  w.stg = s;
+  w.stg = s; s += 1024;
   w.Nm = Nmax;
-  w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay; w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
+  if (SH) {
+    const size_t S = (size_t)Nmax * (2 * K + 1);
+    w.cs = s; s += 2 * S;
+    w.ax = s; w.ay = s + S + 64; w.g2p = s;
+    const size_t axy = 2 * (S + 64), g2 = 2 * (size_t)Nmax * (K + 1);
+    s += (axy > g2 ? axy : g2);
+    w.cellP = s;
+  } else {
+    w.cs = slab + L.cs; w.ax = slab + L.ax; w.ay = slab + L.ay; w.cellP = slab + L.cellP; w.g2p = slab + L.g2p;
+  }
   w.terms = slab + L.terms; w.cg = slab + L.cg; w.fold = slab + L.fold;
   w.nterm = reinterpret_cast<int*>(slab + L.nterm); w.rank = reinterpret_cast<int*>(slab + L.rank);
   w.TS = L.TS;
@@ -656,7 +673,7 @@ wave_penalty_kernel(const __grid_constant__ WParams kp, BatchDev bt, WaveDev wd,
     const int p0 = bt.piece_off[b], N = bt.piece_off[b + 1] - p0;
     const int stage = s->stage;
     Warp w;
-    pen_carve(w, kp.L, smem, slab, kp.Nmax, N, kp.P.sparseResolution);
+    pen_carve<false>(w, kp.L, smem, slab, kp.Nmax, N, kp.P.sparseResolution);
     w.cf = wd.cf + 12 * (size_t)p0;
     w.gC = wd.gC + 12 * (size_t)p0;
     w.sx = bt.start_xytheta[3 * (size_t)b]; w.sy = bt.start_xytheta[3 * (size_t)b + 1];
@@ -1264,7 +1281,8 @@ __global__ void wave_cost_finish_kernel(const __grid_constant__ WParams kp, Batc
 
 // attachPenaltyFunctional on given coefficients (BASELINE configs[2]), one CTA per trajectory, reading the caller's
 // coefficient / duration arrays and accumulating straight into the caller's gradient arrays.
-__global__ void __launch_bounds__(PEN_NT, 3)
+template <int NT, int MINB, bool SH>
+__global__ void __launch_bounds__(NT, MINB)
 penalty_cta_kernel(const __grid_constant__ WParams kp, int B, const int* piece_off, const double* coeffs, const double* Ts,
                    const double* start_xy, const double* final_xy, double* cost, double* gradC, double* gradT, double* err, double* slabs) {
   extern __shared__ __align__(16) double smem[];
@@ -1278,7 +1296,7 @@ penalty_cta_kernel(const __grid_constant__ WParams kp, int B, const int* piece_o
       continue;
     }
     Warp w;
-    pen_carve(w, kp.L, smem, slab, kp.Nmax, N, kp.P.sparseResolution);
+    pen_carve<SH>(w, kp.L, smem, slab, kp.Nmax, N, kp.P.sparseResolution);
     w.cf = const_cast<double*>(coeffs) + 12 * (size_t)p0;
     w.gC = gradC + 12 * (size_t)p0;
     w.sx = start_xy[2 * b]; w.sy = start_xy[2 * b + 1];
@@ -1286,12 +1304,12 @@ penalty_cta_kernel(const __grid_constant__ WParams kp, int B, const int* piece_o
     for (int d = 0; d < 2; d++) { w.lam[d] = kp.P.EqualLambda[d]; w.rho[d] = kp.P.EqualRho[d]; }
     w.safeDis = kp.P.safeDis;
     w.init_pos = nullptr;
-    __syncthreads();
-    for (int i = tid; i < 12 * N; i += PEN_NT) w.gC[i] = 0.0;
-    for (int i = tid; i < N; i += PEN_NT) { w.T1[i] = Ts[p0 + i]; w.gT[i] = 0.0; }
-    __syncthreads();
-    const double f = penalty_passes_t<PEN_NT>(w, kp.P, kp.map, 1, 0.0);
-    for (int i = tid; i < N; i += PEN_NT) gradT[p0 + i] = w.gT[i];
+    tsync<NT>();
+    for (int i = tid; i < 12 * N; i += NT) w.gC[i] = 0.0;
+    for (int i = tid; i < N; i += NT) { w.T1[i] = Ts[p0 + i]; w.gT[i] = 0.0; }
+    tsync<NT>();
+    const double f = penalty_passes_t<NT, SH>(w, kp.P, kp.map, 1, 0.0);
+    for (int i = tid; i < N; i += NT) gradT[p0 + i] = w.gT[i];
     if (tid == 0) { cost[b] = f; err[2 * b] = w.err[0]; err[2 * b + 1] = w.err[1]; }
   }
 }
