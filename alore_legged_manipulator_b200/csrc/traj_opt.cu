@@ -224,42 +224,6 @@ cost_kernel(const __grid_constant__ KParams kp, BatchDev bt, int stage, const do
   }
 }
 
-// attachPenaltyFunctional on given coefficients (BASELINE config 3).
-#ifndef ALORE_PEN_MINBLOCKS
-#define ALORE_PEN_MINBLOCKS 8
-#endif
-__global__ void __launch_bounds__(32, ALORE_PEN_MINBLOCKS)
-penalty_kernel(const __grid_constant__ KParams kp, int B, const int* piece_off, const double* coeffs, const double* Ts,
-               const double* start_xy, const double* final_xy, double* cost, double* gradC, double* gradT, double* err,
-               double* slabs, int* counter) {
-  extern __shared__ __align__(16) double smem[];
-  double* slab = slabs + (size_t)blockIdx.x * kp.L.total;
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    const int b = next_job(counter, lane);
-    if (b >= B) break;
-    const int p0 = piece_off[b];
-    const int N = piece_off[b + 1] - p0;
-    Warp w;
-    carve(w, kp.L, smem, slab, slab, N, kp.P.sparseResolution);
-    w.sx = start_xy[2 * b]; w.sy = start_xy[2 * b + 1];
-    w.fx = final_xy[2 * b]; w.fy = final_xy[2 * b + 1];
-    for (int d = 0; d < 2; d++) { w.lam[d] = kp.P.EqualLambda[d]; w.rho[d] = kp.P.EqualRho[d]; }
-    w.safeDis = kp.P.safeDis;
-    w.time_weight = kp.P.pw_time;
-    w.init_pos = nullptr;
-    const double* c = coeffs + 12 * (size_t)p0;
-    for (int i = lane; i < 12 * N; i += 32) { w.cf[i] = c[i]; w.gC[i] = 0.0; }
-    for (int i = lane; i < N; i += 32) { w.T1[i] = Ts[p0 + i]; w.gT[i] = 0.0; }
-    __syncwarp();
-    const double f = penalty_passes(w, kp.P, kp.map, 1, 0.0);
-    for (int i = lane; i < 12 * N; i += 32) gradC[12 * (size_t)p0 + i] = w.gC[i];
-    for (int i = lane; i < N; i += 32) gradT[p0 + i] = w.gT[i];
-    if (lane == 0) { cost[b] = f; err[2 * b] = w.err[0]; err[2 * b + 1] = w.err[1]; }
-    __syncwarp();
-  }
-}
-
 __global__ void __launch_bounds__(32)
 collision_kernel(const __grid_constant__ KParams kp, int B, const int* piece_off, const double* coeffs, const double* Ts,
                  const double* start_xy, int* collided, double* min_dist, double* slabs, int* counter) {
