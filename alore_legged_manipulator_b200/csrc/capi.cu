@@ -50,6 +50,7 @@ void alore_destroy(alore_ctx* ctx) {
   if (ctx->d_dist) cudaFree(ctx->d_dist);
   if (ctx->d_row) cudaFree(ctx->d_row);
   if (ctx->d_blk) cudaFree(ctx->d_blk);
+  if (ctx->d_band) cudaFree(ctx->d_band);
   if (ctx->opt_scratch) cudaFree(ctx->opt_scratch);
   if (ctx->opt_hist) cudaFree(ctx->opt_hist);
   if (ctx->batch_pool) cudaFree(ctx->batch_pool);

@@ -30,6 +30,8 @@ struct alore_ctx {
   int16_t* d_row = nullptr;      // window-local signed row distances, pitch row_pitch
   uint32_t* d_blk = nullptr;     // per (32-row block, column): lo16 = min g+ , hi16 = min g-
   size_t row_cap = 0, blk_cap = 0;
+  void* d_band = nullptr;        // far-cell masks of the ESDF superband envelope kernel (K2e)
+  size_t band_cap = 0;
   int row_pitch = 0;
   int win[4] = {0, 0, -1, -1};   // min_x, min_y, max_x, max_y of the last update
   int last_ref_compat = 1;

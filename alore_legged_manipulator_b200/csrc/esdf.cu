@@ -15,16 +15,25 @@
 //                         main sweep  — per thread a register window of its column (tile + halo staged in shared
 //                                       memory): the first 8 search steps without loads or branches;
 //                         deferred    — cells that need more (Occupied cells, longer searches) are compacted in
-//                                       shared memory and finished with full lanes: expanding search with the
-//                                       t*t >= best cut-off, then a block-/super-block-pruned search with lower and
-//                                       upper bounds from the minima, a Lipschitz bound chained along a column;
+//                                       shared memory and finished with full lanes: expanding search inside the
+//                                       32-row halo with the t*t >= best cut-off;
+//                         far         — cells whose search leaves the halo (and 32-row bands that deferred every
+//                                       cell) are handed to K2e through one mask word per (band, column) and one flag
+//                                       per tile (ALORE_ESDF_NO_BAND=1: block-/super-block-pruned search in K2);
 //                       then dist = gi*sqrt(val) and the reference's pos/neg combine (sdf_map.cpp:671-679).
+//   K2e esdf_band_kernel  FAR cells: one thread per (32- or 64-row band, column) streams the band's candidate rows
+//                       (selected with the block minima) through Felzenszwalb's stack restricted to what the band can
+//                       see, then answers the band's rows by a pointer walk — O(reach + band) per band instead of
+//                       O(reach) per cell; exact integer tests evaluated in FP64 (all products < 2^53).
 //   K2q esdf_quirk_col  ref_compat: window-local column 0 is recomputed from the aliased input the
 //                       reference actually reads; side stream.
 // All arithmetic on squared distances is int32 (exact); the only FP ops are sqrt.rn.f64, mul.rn.f64 and
 // add.rn.f64, IEEE-identical to the CPU.  Traffic: 1 B/cell in, 2+2 B/cell intermediate (L2-resident at 4096^2),
-// 8 B/cell out; on cluttered maps the kernels are ALU-issue bound at 0.40 of the 13 B/cell HBM roofline, on maps
-// with large empty / solid regions the O(distance) search dominates.
+// 8 B/cell out; on cluttered maps the kernels are ALU-issue bound at 0.37 of the 13 B/cell HBM roofline, on maps
+// with large empty / solid regions K2e dominates.
+#include <algorithm>
+#include <vector>
+#include <cstdio>
 #include <cfloat>
 #include <cstdlib>
 #include <mutex>
@@ -434,6 +443,256 @@ __device__ __forceinline__ double esdf_value(int best, bool neg, double gi) {
              : dv;
 }
 
+// Superband envelope (K2e): the exact column transform for the FAR cells of one column and one kind inside a superband
+// of 32 * ENV_NJ rows, all at once.
+//
+// The expanding search pays O(distance to the nearest seed) per cell; in large empty or solid regions every cell
+// repeats nearly the same walk.  Here the candidate rows of the whole superband [lo, hi] are selected once with the
+// block minima (per 32-row sub-band j an upper bound U_j valid for each of its far rows: a block can matter only if
+// d_near(j, block)^2 + min g^2 <= U_j for some j), streamed in ascending order through Felzenszwalb's stack
+// (sdf_map.cpp:682-715) — the intersection test done by integer cross-multiplication, exact and division-free:
+//     site q is dominated by (p, r)  <=>  (f_q - f_p)(r - q) >= (f_r - f_q)(q - p),   f_x = g(x)^2 + x^2
+// — restricted to what the band can see:
+//   * a new site is stored only if it beats the current top at X = hi (its range lies right of the top's: a site that
+//     loses at hi owns nothing in the band, and neither does any later site it would have shielded),
+//   * a stack of ONE site is replaced by a new site that is STRICTLY better at X = lo (the old one then loses on the
+//     whole band).  The bottom pair only changes when the second site is the one just pushed, so this is the complete
+//     bottom trim, and the stack base never moves.
+// Both rules keep the chain convex and keep every owner of a row in [lo, hi] (checked against brute force on 2·10^5
+// random columns, ties included); the stack never held more than (hi - lo + 1) + 2 sites.  The top two sites live in
+// registers: a row costs no dependent memory access unless it pops.  The far rows are then answered by a pointer walk
+// (owners are monotone).  O(candidate rows + band rows) per (superband, column).
+constexpr int ENV_CAP = 512;                    // stack capacity; (rows of the superband) + 2 is what the band can need
+// rows per superband = 32 * ENV_NJ (template parameter: 2, 4 or 8 sub-bands; chosen by the host from the window size)
+template <bool SQ>
+__device__ __forceinline__ void esdf_store(int best, bool neg, int X, int y, int NY, double* __restrict__ dist, int gly, int min_x,
+                                           int min_y, double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  if (SQ) {
+    const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
+    pos_sq[(size_t)X * NY + y] = neg ? 0 : v;
+    neg_sq[(size_t)X * NY + y] = neg ? v : 0;
+  } else {
+    dist[(size_t)(X + min_x) * gly + y + min_y] = esdf_value(best, neg, gi);
+  }
+}
+
+// upper bound for every row of [lo, hi] (one kind, one column) from the rows' own in-row distance and the block minima
+__device__ __forceinline__ int esdf_band_bound(const uint32_t* __restrict__ blkc, int blk_pitch, int nblk, int NX, int lo, int hi,
+                                               bool neg, int own_max) {
+  auto mg = [&](int b) -> int {
+    const uint32_t m = blkc[(size_t)b * blk_pitch];
+    return neg ? (int)(m >> 16) : (int)(m & 0xffffu);
+  };
+  const int bL = lo / BLK, bH = hi / BLK;
+  long long U = own_max < SENT ? (long long)own_max * own_max : (long long)0x7fffffff;   // val(X) <= g(X)^2
+  for (int b = bL; b <= bH; b++) {
+    const int m = mg(b);
+    if (m < SENT) {
+      const int b0 = b * BLK, b1 = min(b0 + BLK - 1, NX - 1);
+      const int df = max(hi - b0, b1 - lo);
+      U = min(U, (long long)df * df + (long long)m * m);
+    }
+  }
+  for (int d = 1;; d++) {
+    const int ba = bL - d, bb = bH + d;
+    bool any = false;
+    if (ba >= 0) {
+      const int b0 = ba * BLK, b1 = b0 + BLK - 1;
+      const int dn = lo - b1;
+      if ((long long)dn * dn < U) {
+        any = true;
+        const int m = mg(ba);
+        if (m < SENT) { const int df = hi - b0; U = min(U, (long long)df * df + (long long)m * m); }
+      }
+    }
+    if (bb < nblk) {
+      const int b0 = bb * BLK, b1 = min(b0 + BLK - 1, NX - 1);
+      const int dn = b0 - hi;
+      if ((long long)dn * dn < U) {
+        any = true;
+        const int m = mg(bb);
+        if (m < SENT) { const int df = b1 - lo; U = min(U, (long long)df * df + (long long)m * m); }
+      }
+    }
+    if (!any) break;
+  }
+  return (int)U;
+}
+
+template <bool SQ, int ENV_NJ>
+__device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch,
+                                                int NX, int NY, const uint32_t* __restrict__ fm, int mpitch, int nbands, int j0, int j1,
+                                                unsigned live, bool neg, int y, double* __restrict__ dist, int gly, int min_x, int min_y, double gi,
+                                                int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  const int nblk = (NX + BLK - 1) / BLK;
+  const uint32_t* blkc = blk + y;
+  const int16_t* Rc = R + y;
+  const unsigned flip = neg ? 0u : 0xffffffffu;               // rows of this kind: far & (occupied ^ flip)
+  auto rows_of = [&](int j) -> unsigned {                     // masks of a tile without far cells are not written by K2
+    if (!((live >> (j - j0)) & 1u)) return 0u;
+    return fm[(size_t)j * mpitch] & (fm[(size_t)(nbands + j) * mpitch] ^ flip);
+  };
+  // 1. per sub-band: its far rows of this kind, their bound U_j; the candidate range is the hull of the reaches
+  int Uj[ENV_NJ], loj[ENV_NJ], hij[ENV_NJ];
+  int lo = NX, hi = -1, cl = NX, ch = -1;
+  for (int j = j0; j < j1; j++) {
+    const unsigned mk = rows_of(j);
+    int U = -1, l = NX, h = -1;
+    if (mk) {
+      l = (j << 5) + __ffs(mk) - 1;
+      h = (j << 5) + 31 - __clz(mk);
+      U = esdf_band_bound(blkc, blk_pitch, nblk, NX, l, h, neg, SENT);
+      const int reach = (int)sqrt((double)U) + 1;
+      cl = min(cl, l - reach); ch = max(ch, h + reach);
+      lo = min(lo, l); hi = h;
+    }
+    Uj[j - j0] = U; loj[j - j0] = l; hij[j - j0] = h;
+  }
+  cl = max(cl, 0); ch = min(ch, NX - 1);
+  // 2. the stack of the candidate rows, ascending; top two sites in registers.  All products are integers below 2^53,
+  //    so the tests are done in FP64 (exact) — one DMUL where the integer pipe needs four IMADs.
+  int sv[ENV_CAP];
+  unsigned sf[ENV_CAP];
+  int top = -1;
+  double vt = 0.0, vp = 0.0, ft = 0.0, fp = 0.0;
+  bool overflow = false;
+  const double lo2 = 2.0 * lo, hi2 = 2.0 * hi;
+  unsigned Umax = 0u;
+#pragma unroll
+  for (int j = 0; j < ENV_NJ; j++)
+    if (j < j1 - j0 && Uj[j] >= 0) Umax = max(Umax, (unsigned)Uj[j]);
+  for (int b = cl / BLK; b <= ch / BLK && !overflow; b++) {
+    const int b0 = b * BLK, b1 = min(b0 + BLK - 1, NX - 1);
+    const uint32_t mm = blkc[(size_t)b * blk_pitch];
+    const int m = neg ? (int)(mm >> 16) : (int)(mm & 0xffffu);
+    if (m >= SENT) continue;
+    bool need = false;
+    for (int j = 0; j < j1 - j0 && !need; j++) {
+      if (Uj[j] < 0) continue;
+      const int dn = b1 < loj[j] ? loj[j] - b1 : (b0 > hij[j] ? b0 - hij[j] : 0);
+      need = (long long)dn * dn + (long long)m * m <= (long long)Uj[j];
+    }
+    if (!need) continue;
+    int rr[8], rn[8];
+    const int pad = neg ? -SENT : SENT;
+#pragma unroll
+    for (int i = 0; i < 8; i++) rr[i] = (b0 + i <= b1) ? (int)Rc[(size_t)(b0 + i) * pitch] : pad;
+#pragma unroll 1
+    for (int xb = b0; xb <= b1; xb += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) rn[i] = (xb + 8 + i <= b1) ? (int)Rc[(size_t)(xb + 8 + i) * pitch] : pad;   // next batch in flight
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int x = xb + i;
+        const int g = neg ? max(-rr[i], 0) : max(rr[i], 0);    // a row of the other kind is a seed itself
+        const int dnr = max(max(lo - x, x - hi), 0);
+        // no seed of this kind in the row, or a site that cannot reach any far row of the band: never an owner
+        if (g >= SENT || (unsigned)(dnr * dnr) + (unsigned)(g * g) > Umax) continue;
+        const unsigned fi = (unsigned)(g * g) + (unsigned)(x * x);
+        const double f = (double)fi, xd = (double)x;
+        double bx = xd - vt, cf = f - ft;
+        while (top >= 1 && (ft - fp) * bx >= cf * (vt - vp)) {
+          top--;
+          vt = vp; ft = fp;
+          if (top >= 1) { vp = (double)sv[top - 1]; fp = (double)sf[top - 1]; }
+          bx = xd - vt; cf = f - ft;
+        }
+        if (top >= 0 && cf >= hi2 * bx) continue;              // loses to the top at X = hi
+        if (top == 0 && cf < lo2 * bx) {                         // the only site loses the whole band
+          sv[0] = x; sf[0] = fi;
+          vt = xd; ft = f;
+          continue;
+        }
+        if (top + 1 >= ENV_CAP) { overflow = true; break; }
+        ++top;
+        sv[top] = x; sf[top] = fi;
+        vp = vt; fp = ft; vt = xd; ft = f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) rr[i] = rn[i];
+      if (overflow) break;
+    }
+  }
+  if (overflow) return false;
+  // 3. the far rows of this kind, ascending, pointer walk
+  int k = 0;
+  double vk = 0.0, fk = 0.0, vn = 0.0, fn = 0.0;
+  if (top >= 0) { vk = (double)sv[0]; fk = (double)sf[0]; }
+  if (top >= 1) { vn = (double)sv[1]; fn = (double)sf[1]; }
+  for (int j = j0; j < j1; j++) {
+    unsigned mk = rows_of(j);
+    while (mk) {
+      const int X = (j << 5) + __ffs(mk) - 1;
+      mk &= mk - 1;
+      int best = SQ_SENT;
+      if (top >= 0) {
+        const double X2 = 2.0 * X;
+        double ck = fk - X2 * vk;                              // cost_k(X) = f_k - 2 X v_k + X^2
+        while (k < top) {
+          const double cn = fn - X2 * vn;
+          if (cn > ck) break;
+          ck = cn; k++;
+          vk = vn; fk = fn;
+          if (k < top) { vn = (double)sv[k + 1]; fn = (double)sf[k + 1]; }
+        }
+        const double v = ck + (double)X * (double)X;
+        best = v < (double)SQ_SENT ? (int)v : SQ_SENT;
+      }
+      esdf_store<SQ>(best, neg, X, y, NY, dist, gly, min_x, min_y, gi, pos_sq, neg_sq);
+    }
+  }
+  return true;
+}
+
+// K2e: one thread per (superband of 32 * ENV_NJ rows, column).  far_mask[X / 32][y] holds the rows K2 left for this kernel,
+// far_mask[nbands + X / 32][y] the Occupied ones among them.
+template <bool SQ, int ENV_NJ>
+__global__ void __launch_bounds__(128)
+esdf_band_kernel(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
+                 const uint32_t* __restrict__ far_mask, int mpitch, int nbands, double* __restrict__ dist, int gly, int min_x, int min_y,
+                 double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  const int y = blockIdx.x * 128 + threadIdx.x;
+  if (y >= NY) return;
+  const uint32_t* fm = far_mask + y;
+  const int j0 = blockIdx.y * ENV_NJ, j1 = min(j0 + ENV_NJ, (NX + 31) / 32);
+  // tiles of K2 (64 rows x 128 columns) that left nothing: one flag each, their masks are not even written
+  const int* flag = reinterpret_cast<const int*>(far_mask + (size_t)2 * nbands * mpitch) + blockIdx.x;
+  unsigned live = 0u;
+#pragma unroll
+  for (int i = 0; i < ENV_NJ; i++)
+    if (j0 + i < j1 && flag[(size_t)((j0 + i) >> 1) * gridDim.x]) live |= 1u << i;
+  if (!live) return;
+  unsigned any_p = 0u, any_n = 0u;
+#pragma unroll
+  for (int i = 0; i < ENV_NJ; i++) {
+    if (!((live >> i) & 1u)) continue;
+    const unsigned f = fm[(size_t)(j0 + i) * mpitch], o = fm[(size_t)(nbands + j0 + i) * mpitch];
+    any_p |= f & ~o;
+    any_n |= f & o;
+  }
+  bool ok_p = true, ok_n = true;
+  if (any_p) ok_p = esdf_band_envelope<SQ, ENV_NJ>(R, pitch, blk, blk_pitch, NX, NY, fm, mpitch, nbands, j0, j1, live, false, y, dist, gly, min_x, min_y, gi, pos_sq, neg_sq);
+  if (any_n) ok_n = esdf_band_envelope<SQ, ENV_NJ>(R, pitch, blk, blk_pitch, NX, NY, fm, mpitch, nbands, j0, j1, live, true, y, dist, gly, min_x, min_y, gi, pos_sq, neg_sq);
+  if (ok_p && ok_n) return;
+  // a stack that outgrew its array (never seen): plain exact search for the rows of that kind
+  for (int j = j0; j < j1; j++) {
+    unsigned mk = ((live >> (j - j0)) & 1u) ? fm[(size_t)j * mpitch] : 0u;
+    while (mk) {
+      const int X = (j << 5) + __ffs(mk) - 1;
+      mk &= mk - 1;
+      const int r0 = R[(size_t)X * pitch + y];
+      const bool neg = r0 < 0;
+      if (neg ? ok_n : ok_p) continue;
+      int best = r0 * r0;
+      for (int t = 1; t * t < best && (X - t >= 0 || X + t < NX); t++) {
+        if (X - t >= 0) { const int r = R[(size_t)(X - t) * pitch + y]; const int g = neg ? max(-r, 0) : max(r, 0); best = min(best, g * g + t * t); }
+        if (X + t < NX) { const int r = R[(size_t)(X + t) * pitch + y]; const int g = neg ? max(-r, 0) : max(r, 0); best = min(best, g * g + t * t); }
+      }
+      esdf_store<SQ>(best, neg, X, y, NY, dist, gly, min_x, min_y, gi, pos_sq, neg_sq);
+    }
+  }
+}
+
 // K2: column pass.  grid (ceil(NY/TY), ceil(NX/TX)), 256 threads = 128 columns x 2 row halves.
 // A probe of row x' contributes t^2 + g(x')^2 where g is the row distance of the SAME kind as the query cell
 // (0 for the other kind).  Free/unknown query cells (the overwhelming majority) take the fast path: g = max(R, 0),
@@ -445,8 +704,13 @@ template <bool SQ>
 __global__ void __launch_bounds__(256)
 esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
               double* __restrict__ dist, int gly, int min_x, int min_y, double gi, int ref_compat,
-              int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+              int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq, uint32_t* __restrict__ far_mask) {
   __shared__ __align__(16) int16_t S[TX + 2 * HALO][TY];
+  __shared__ unsigned s_far[256], s_farneg[256];                 // per thread: rows of its 32-row band left to K2e / the Occupied ones
+  __shared__ int s_anyfar;
+  s_far[threadIdx.x] = 0u;
+  s_farneg[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) s_anyfar = 0;
   __shared__ double s_sqrt[SQ ? 1 : SQRT_SMEM];
   constexpr int DEF_CAP = 2048;                                  // deferred cells held in the list (25 % of a tile)
   __shared__ unsigned short s_list[DEF_CAP];
@@ -533,6 +797,20 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
     }
 #undef ALORE_K2_CELL
   }
+  // ---- a band that defers (nearly) all of its cells lies in a large empty / solid region: straight to K2e -----------
+#ifndef ALORE_K2_BAND_MIN
+#define ALORE_K2_BAND_MIN 32
+#endif
+  if (far_mask && __popc(defer) >= ALORE_K2_BAND_MIN) {
+    unsigned occm = 0u;                                               // the Occupied rows among them
+    const int16_t* cs = &S[Xb - rlo][ty];
+#pragma unroll
+    for (int r = 0; r < 32; r++) occm |= (unsigned)(cs[r * TY] < 0) << r;
+    s_far[threadIdx.x] = defer;                                       // own slot; the list below only ORs into it
+    s_farneg[threadIdx.x] = occm & defer;
+    s_anyfar = 1;
+    defer = 0u;
+  }
   // ---- deferred cells: compact (thread, row) pairs into shared memory, then one cell per thread per round -----------
   {
     const int cntme = __popc(defer);
@@ -599,8 +877,15 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
         if (X + t < NX) { const int b = max(-(int)col[t * TY], 0); best = min(best, b * b + tt); }
       }
     }
-    if (t * t < best && (X - t >= 0 || X + t < NX))      // rows left to look at: beyond the halo, or switched early
+    if (t * t < best && (X - t >= 0 || X + t < NX)) {    // rows left to look at: beyond the halo, or switched early
+      if (far_mask) {                                    // FAR cell: left to the superband envelope kernel (K2e)
+        atomicOr(&s_far[th], 1u << r);
+        if (neg) atomicOr(&s_farneg[th], 1u << r);
+        s_anyfar = 1;
+        continue;
+      }
       best = esdf_far_search(R, pitch, blk, blk_pitch, NX, X, yy, neg, best, t);
+    }
     if (own) { prev_best = best; prev_r = r; prev_neg = neg; }
     if (SQ) {
       const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
@@ -614,6 +899,16 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
       const double dv = __dmul_rn(gi, root);                     // grid_interval_ * std::sqrt(val)
       dist[(size_t)(X + min_x) * gly + yy + min_y] = neg ? __dadd_rn(0.0, __dadd_rn(-dv, gi)) : dv;   // all = pos(=0); all += (-neg + gi)
     }
+  }
+  if (far_mask) {                                        // dense: every (32-row band, column) of the tile is written
+    __syncthreads();
+    const int anyfar = s_anyfar;
+    if (anyfar && y < pitch) {
+      far_mask[(size_t)(blockIdx.y * 2 + half) * pitch + y] = s_far[threadIdx.x];
+      far_mask[(size_t)(gridDim.y * 2 + blockIdx.y * 2 + half) * pitch + y] = s_farneg[threadIdx.x];
+    }
+    if (threadIdx.x == 0)                                // one flag per tile, behind the two mask planes
+      reinterpret_cast<int*>(far_mask + (size_t)4 * gridDim.y * pitch)[blockIdx.y * gridDim.x + blockIdx.x] = anyfar;
   }
 }
 
@@ -846,13 +1141,44 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_col_dc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem));
     ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_col_dc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem));
   }
+  // far-cell masks of the superband envelope kernel (K2e): one word per (32-row band, column), rewritten by every K2
+  uint32_t* far_mask = nullptr;
+  if (!use_dc && !getenv("ALORE_ESDF_NO_BAND")) {
+    const size_t need = ((size_t)(4 * ((NX + TX - 1) / TX)) * pitch + (size_t)((NX + TX - 1) / TX) * ((NY + TY - 1) / TY)) * sizeof(uint32_t);   // far rows, the Occupied ones among them, one flag per K2 tile
+    if (need > ctx->band_cap) {
+      if (ctx->d_band) { cudaDeviceSynchronize(); cudaFree(ctx->d_band); }
+      ctx->d_band = nullptr; ctx->band_cap = 0;
+      ALORE_CUDA(ctx, cudaMalloc(&ctx->d_band, need));
+      ctx->band_cap = need;
+    }
+    far_mask = static_cast<uint32_t*>(ctx->d_band);
+  }
+  // superband height: tall bands amortise the candidate scan (O(reach + band) per thread), short ones give more threads
+  int band_nj = (size_t)NX * NY < ((size_t)8 << 20) ? 1 : 2;          // measured: 32 rows on 2048^2 (more threads), 64 on 16 Mcells
+  if (const char* e = getenv("ALORE_ESDF_SB")) { const int v = atoi(e); band_nj = v >= 256 ? 8 : (v >= 128 ? 4 : (v >= 64 ? 2 : 1)); }
+  const dim3 band_grid((NY + 127) / 128, (NX + 32 * band_nj - 1) / (32 * band_nj));
   if (sq) {
     if (use_dc)
       esdf_col_dc<true><<<dc_grid, 1024, dc_smem, st>>>(ctx->d_row, pitch, NX, NY, lgDC, n_pow2, d_dist, g.gly, min_x, min_y, g.grid_interval,
                                                         ref_compat, d_pos_sq, d_neg_sq);
     else
-    esdf_col_pass<true><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
-                                              g.grid_interval, ref_compat, d_pos_sq, d_neg_sq);
+    {
+      esdf_col_pass<true><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                                g.grid_interval, ref_compat, d_pos_sq, d_neg_sq, far_mask);
+      if (far_mask) {
+        switch (band_nj) {
+          case 8: esdf_band_kernel<true, 8><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                          min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
+          case 4: esdf_band_kernel<true, 4><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                          min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
+          case 2: esdf_band_kernel<true, 2><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                          min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
+          default: esdf_band_kernel<true, 1><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                          min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
+        }
+        ctx->launches++;
+      }
+    }
     ctx->launches++;
     if (quirk) {
       esdf_quirk_col<true><<<(NX + 127) / 128, 128, 0, st>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
@@ -873,8 +1199,23 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
       esdf_col_dc<false><<<dc_grid, 1024, dc_smem, st>>>(ctx->d_row, pitch, NX, NY, lgDC, n_pow2, d_dist, g.gly, min_x, min_y, g.grid_interval,
                                                          ref_compat, nullptr, nullptr);
     else
-    esdf_col_pass<false><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
-                                               g.grid_interval, ref_compat, nullptr, nullptr);
+    {
+      esdf_col_pass<false><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+                                                 g.grid_interval, ref_compat, nullptr, nullptr, far_mask);
+      if (far_mask) {
+        switch (band_nj) {
+          case 8: esdf_band_kernel<false, 8><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                           min_x, min_y, g.grid_interval, nullptr, nullptr); break;
+          case 4: esdf_band_kernel<false, 4><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                           min_x, min_y, g.grid_interval, nullptr, nullptr); break;
+          case 2: esdf_band_kernel<false, 2><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                           min_x, min_y, g.grid_interval, nullptr, nullptr); break;
+          default: esdf_band_kernel<false, 1><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+                                                           min_x, min_y, g.grid_interval, nullptr, nullptr); break;
+        }
+        ctx->launches++;
+      }
+    }
     ctx->launches++;
     if (side) ALORE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
   }
