@@ -127,6 +127,24 @@ class CandidateBatch:
     def total_pieces(self) -> int:
         return int(self.piece_off[-1])
 
+    def _arrays(self):
+        return (self.piece_off, self.inner_pts, self.init_T, self.inner_init_pos, self.start_state, self.final_state,
+                self.start_xytheta, self.final_xytheta, self.if_cut)
+
+    def pin(self, ctx: "Context") -> "CandidateBatch":
+        """Page-locks the batch's arrays (a front end that fills the same staging buffers every tick does this once)."""
+        self._pins = getattr(self, "_pins", [])
+        for a in self._arrays():
+            if a.nbytes and ctx.lib.alore_host_register(ctx.h, a.ctypes.data, a.nbytes) == 0:
+                self._pins.append((ctx, a))
+        return self
+
+    def unpin(self):
+        for ctx, a in getattr(self, "_pins", []):
+            if ctx.h:
+                ctx.lib.alore_host_unregister(ctx.h, a.ctypes.data)
+        self._pins = []
+
     def n_vars(self) -> int:
         return 3 * self.total_pieces - self.B
 
@@ -168,18 +186,46 @@ class CandidateBatch:
 
 
 class ResultBatch:
-    def __init__(self, cands: CandidateBatch):
-        B, tot = cands.B, cands.total_pieces
-        self.ok = np.zeros(B, np.int32)
-        self.status = np.zeros(B, np.int32)
-        self.replans = np.zeros(B, np.int32)
-        self.alm_iters = np.zeros(B, np.int32)
-        self.evals = np.zeros(B, np.int32)
-        self.cost = np.zeros(B)
-        self.inner_pts = np.zeros((max(tot - B, 1), 2))
-        self.tail_s = np.zeros(B)
-        self.piece_T = np.zeros(tot)
-        self.coeffs = np.zeros((tot, 6, 2))
+    """Host-side results of one batch.  `capacity=(B, total_pieces)` allocates a REUSABLE result store: a planner that
+    replans every tick keeps one (page-locked with `pin`) and passes it as `out=` to `minco_plan_batch`, which binds the
+    public arrays to the leading part the tick's candidates need."""
+
+    _FIELDS = ("ok", "status", "replans", "alm_iters", "evals", "cost", "inner_pts", "tail_s", "piece_T", "coeffs")
+
+    def __init__(self, cands: CandidateBatch | None = None, *, capacity: tuple[int, int] | None = None):
+        B, tot = capacity if capacity is not None else (cands.B, cands.total_pieces)
+        self.capacity = (int(B), int(tot))
+        self._base = {
+            "ok": np.zeros(B, np.int32), "status": np.zeros(B, np.int32), "replans": np.zeros(B, np.int32),
+            "alm_iters": np.zeros(B, np.int32), "evals": np.zeros(B, np.int32), "cost": np.zeros(B),
+            "inner_pts": np.zeros((max(tot - 1, 1), 2)), "tail_s": np.zeros(B), "piece_T": np.zeros(tot),
+            "coeffs": np.zeros((tot, 6, 2)),
+        }
+        self._pins: list = []
+        self.bind(B, tot)
+
+    def bind(self, B: int, tot: int) -> "ResultBatch":
+        """Points the public arrays at the leading (B, tot) part of the store."""
+        cb, ct = self.capacity
+        if B > cb or tot > ct:
+            raise ValueError(f"result store holds {cb} candidates / {ct} pieces, batch needs {B} / {tot}")
+        n = {"inner_pts": max(tot - B, 1), "piece_T": tot, "coeffs": tot}
+        for f in self._FIELDS:
+            setattr(self, f, self._base[f][: n.get(f, B)])
+        return self
+
+    def pin(self, ctx: "Context") -> "ResultBatch":
+        """Page-locks the store (cudaHostRegister through the C ABI); released by unpin() or when `ctx` is closed."""
+        for a in self._base.values():
+            if ctx.lib.alore_host_register(ctx.h, a.ctypes.data, a.nbytes) == 0:
+                self._pins.append((ctx, a))
+        return self
+
+    def unpin(self):
+        for ctx, a in self._pins:
+            if ctx.h:
+                ctx.lib.alore_host_unregister(ctx.h, a.ctypes.data)
+        self._pins = []
 
     def as_struct(self) -> Results:
         return Results(iptr(self.ok), iptr(self.status), iptr(self.replans), iptr(self.alm_iters), iptr(self.evals),

@@ -79,9 +79,10 @@ class MSPlanner:
         res = self.minco_plan_batch(front_end.pack_candidates([flat_traj]))
         return bool(res.ok[0])
 
-    def minco_plan_batch(self, cands: capi.CandidateBatch) -> capi.ResultBatch:
+    def minco_plan_batch(self, cands: capi.CandidateBatch, out: capi.ResultBatch | None = None) -> capi.ResultBatch:
+        """Optimises every candidate of the batch.  `out`: a reusable (optionally page-locked) result store."""
         self.map_._check_owner()
-        res = capi.ResultBatch(cands)
+        res = capi.ResultBatch(cands) if out is None else out.bind(cands.B, cands.total_pieces)
         cs, rs = cands.as_struct(), res.as_struct()
         self.ctx.check(self.ctx.lib.alore_opt_batch(self.ctx.h, C.byref(self.params), C.byref(cs), C.byref(rs)))
         self.last_result, self._cands = res, cands

@@ -430,10 +430,16 @@ def main():
     res0 = batches[0].download()
 
     # ---- end to end through the host-buffer C ABI (same perturbed ticks) -------------------------------------------
+    # host side as a planner keeps it: candidates in page-locked staging arrays, ONE page-locked result store reused
+    # by every tick (a fresh 70 MB numpy result per call costs more in page faults than its PCIe transfer)
+    store = capi.ResultBatch(capacity=(max(tk[1].B for tk in ticks), max(tk[1].total_pieces for tk in ticks))).pin(ctx)
+    for tk in ticks:
+        tk[1].pin(ctx)
+
     def step_e2e(t):
         m.gridmap_[:] = ticks[t][0]
         m.updateESDF2d()
-        r = pl.minco_plan_batch(ticks[t][1])
+        r = pl.minco_plan_batch(ticks[t][1], out=store)
         sharding.gather_best(*sharding.local_best(r.cost, r.ok, lo), device="cuda")
         return r
 

@@ -113,3 +113,22 @@ def test_device_penalty_entry_refuses_undeclared_piece_counts(world, ctx):
         torch.cuda.synchronize()
         cost = o[0].cpu().numpy()
         assert np.isfinite(cost[0]) and bool(np.isnan(cost[1])) == want_nan
+
+
+def test_reusable_pinned_result_store_gives_the_same_results(world, ctx):
+    """`minco_plan_batch(cands, out=store)`: one page-locked result store reused by batches of different sizes."""
+    m, prm, pl, grid = world
+    big, small = leg_batch(world, max_legs=48), leg_batch(world, max_legs=20)
+    store = capi.ResultBatch(capacity=(big.B, big.total_pieces)).pin(ctx)
+    try:
+        for cands in (big.pin(ctx), small, big):
+            a = pl.minco_plan_batch(cands)
+            b = pl.minco_plan_batch(cands, out=store)
+            assert b is store and b.coeffs.shape == a.coeffs.shape
+            for f in capi.ResultBatch._FIELDS:
+                assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        with pytest.raises(ValueError):
+            capi.ResultBatch(capacity=(4, 16)).bind(big.B, big.total_pieces)
+    finally:
+        big.unpin()
+        store.unpin()

@@ -89,3 +89,14 @@ def test_oracle_states_the_same_defaults():
     import oracle_lib
     a, b = capi.default_params(), oracle_lib.default_params()
     assert bytes(C.string_at(C.addressof(a), C.sizeof(a))) == bytes(C.string_at(C.addressof(b), C.sizeof(b)))
+
+
+def test_result_store_binds_views_of_one_allocation():
+    r = capi.ResultBatch(capacity=(10, 100))
+    r.bind(4, 30)
+    assert r.ok.shape == (4,) and r.coeffs.shape == (30, 6, 2) and r.inner_pts.shape == (26, 2) and r.piece_T.shape == (30,)
+    assert r.coeffs.ctypes.data == r._base["coeffs"].ctypes.data
+    r.bind(10, 100)
+    assert r.inner_pts.shape == (90, 2)
+    with pytest.raises(ValueError):
+        r.bind(11, 30)
