@@ -32,6 +32,7 @@ struct alore_ctx {
   size_t row_cap = 0, blk_cap = 0;
   void* d_band = nullptr;        // far-cell masks of the ESDF superband envelope kernel (K2e)
   size_t band_cap = 0;
+  int band_epoch = 0;            // flags of K2e are 'set' when they hold the current run's epoch
   int row_pitch = 0;
   int win[4] = {0, 0, -1, -1};   // min_x, min_y, max_x, max_y of the last update
   int last_ref_compat = 1;

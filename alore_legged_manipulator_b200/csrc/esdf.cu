@@ -310,7 +310,10 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
 // shuffles.  grid (ceil(pitch/8/32), ceil(NX/BLK)), 128 threads = 32 column groups x 4 row quarters.
 __device__ __forceinline__ unsigned max0_s2(unsigned v) { return __vmaxs2(v, 0u); }
 __global__ void __launch_bounds__(128)
-esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch) {
+esdf_block_min(const int16_t* __restrict__ R, int pitch, int NX, int NY, uint32_t* __restrict__ blk, int blk_pitch,
+               const int* __restrict__ colflag, int ncol, int epoch) {
+  // after K2 (band path): only the 128-column tiles that left FAR cells need their minima (colflag == this run's epoch)
+  if (colflag && colflag[min(2 * (int)blockIdx.x, ncol - 1)] != epoch && colflag[min(2 * (int)blockIdx.x + 1, ncol - 1)] != epoch) return;
   const int rq = threadIdx.x & 3;
   const int y0 = (blockIdx.x * 32 + (threadIdx.x >> 2)) * 8;
   const bool in = y0 < pitch;
@@ -649,18 +652,18 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
 template <bool SQ, int ENV_NJ>
 __global__ void __launch_bounds__(128)
 esdf_band_kernel(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
-                 const uint32_t* __restrict__ far_mask, int mpitch, int nbands, double* __restrict__ dist, int gly, int min_x, int min_y,
-                 double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+                 const uint32_t* __restrict__ far_mask, int mpitch, int nbands, int epoch, double* __restrict__ dist, int gly, int min_x,
+                 int min_y, double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
   const int y = blockIdx.x * 128 + threadIdx.x;
   if (y >= NY) return;
   const uint32_t* fm = far_mask + y;
   const int j0 = blockIdx.y * ENV_NJ, j1 = min(j0 + ENV_NJ, (NX + 31) / 32);
-  // tiles of K2 (64 rows x 128 columns) that left nothing: one flag each, their masks are not even written
+  // tiles of K2 (64 rows x 128 columns) that left nothing this run (flag != epoch): their masks are not even written
   const int* flag = reinterpret_cast<const int*>(far_mask + (size_t)2 * nbands * mpitch) + blockIdx.x;
   unsigned live = 0u;
 #pragma unroll
   for (int i = 0; i < ENV_NJ; i++)
-    if (j0 + i < j1 && flag[(size_t)((j0 + i) >> 1) * gridDim.x]) live |= 1u << i;
+    if (j0 + i < j1 && flag[(size_t)((j0 + i) >> 1) * gridDim.x] == epoch) live |= 1u << i;
   if (!live) return;
   unsigned any_p = 0u, any_n = 0u;
 #pragma unroll
@@ -704,7 +707,7 @@ template <bool SQ>
 __global__ void __launch_bounds__(256)
 esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch, int NX, int NY,
               double* __restrict__ dist, int gly, int min_x, int min_y, double gi, int ref_compat,
-              int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq, uint32_t* __restrict__ far_mask) {
+              int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq, uint32_t* __restrict__ far_mask, int epoch) {
   __shared__ __align__(16) int16_t S[TX + 2 * HALO][TY];
   __shared__ unsigned s_far[256], s_farneg[256];                 // per thread: rows of its 32-row band left to K2e / the Occupied ones
   __shared__ int s_anyfar;
@@ -797,11 +800,12 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
     }
 #undef ALORE_K2_CELL
   }
-  // ---- a band that defers (nearly) all of its cells lies in a large empty / solid region: straight to K2e -----------
+  // ---- a band that defers all of its cells lies in a large empty / solid region: straight to K2e; so do the bands
+  //      that do not fit the CTA's list (tiles with more than 25 % deferred cells) ------------------------------------
 #ifndef ALORE_K2_BAND_MIN
 #define ALORE_K2_BAND_MIN 32
 #endif
-  if (far_mask && __popc(defer) >= ALORE_K2_BAND_MIN) {
+  auto band_to_far = [&]() {
     unsigned occm = 0u;                                               // the Occupied rows among them
     const int16_t* cs = &S[Xb - rlo][ty];
 #pragma unroll
@@ -810,7 +814,8 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
     s_farneg[threadIdx.x] = occm & defer;
     s_anyfar = 1;
     defer = 0u;
-  }
+  };
+  if (far_mask && __popc(defer) >= ALORE_K2_BAND_MIN) band_to_far();
   // ---- deferred cells: compact (thread, row) pairs into shared memory, then one cell per thread per round -----------
   {
     const int cntme = __popc(defer);
@@ -824,8 +829,9 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
         s_list[base++] = (unsigned short)((threadIdx.x << 5) | r);    // thread (8 bits) : row offset (5 bits)
       }
       defer = 0u;
-    } else {                                                          // list full: the thread keeps its cells
+    } else {                                                          // list full
       for (int i = base; i < min(base + cntme, DEF_CAP); i++) s_list[i] = 0xffffu;   // reserved but unused slots
+      if (far_mask) band_to_far();                                    // ... K2e takes the band (else the thread keeps its cells)
     }
   }
   __syncthreads();
@@ -907,8 +913,11 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
       far_mask[(size_t)(blockIdx.y * 2 + half) * pitch + y] = s_far[threadIdx.x];
       far_mask[(size_t)(gridDim.y * 2 + blockIdx.y * 2 + half) * pitch + y] = s_farneg[threadIdx.x];
     }
-    if (threadIdx.x == 0)                                // one flag per tile, behind the two mask planes
-      reinterpret_cast<int*>(far_mask + (size_t)4 * gridDim.y * pitch)[blockIdx.y * gridDim.x + blockIdx.x] = anyfar;
+    if (anyfar && threadIdx.x == 0) {                    // flags behind the two mask planes: one per tile, one per tile column;
+      int* flags = reinterpret_cast<int*>(far_mask + (size_t)4 * gridDim.y * pitch);   // "set" = this run's epoch, never cleared
+      flags[blockIdx.y * gridDim.x + blockIdx.x] = epoch;
+      flags[gridDim.y * gridDim.x + blockIdx.x] = epoch;
+    }
   }
 }
 
@@ -1029,23 +1038,29 @@ esdf_col_dc(const int16_t* __restrict__ R, int pitch, int NX, int NY, int lgDC, 
 // transform over the virtual column W(j), j in [1, NX]:  W(j) = R(j, 0) for j <= NX-1, W(NX) = R(NX-1, NY-1),
 // evaluated at j = X  (sdf_map.cpp:639-650: index x*update_Y_SIZE + y with y == update_Y_SIZE aliases row x+1).
 template <bool SQ>
-__global__ void esdf_quirk_col(const int16_t* __restrict__ R, int pitch, int NX, int NY, double* __restrict__ dist, int gly,
-                               int min_x, int min_y, double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
-  const int X = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+esdf_quirk_col(const int16_t* __restrict__ R, int pitch, int NX, int NY, double* __restrict__ dist, int gly,
+               int min_x, int min_y, double gi, int32_t* __restrict__ pos_sq, int32_t* __restrict__ neg_sq) {
+  // one WARP per cell: lane l probes the steps t0 + l of the expanding search, the cut-off t^2 >= best is applied per
+  // chunk of 32 steps (extra probes cannot lower an exact minimum)
+  const int lane = threadIdx.x & 31;
+  const int X = 1 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (X > NX - 1) return;
   if (!SQ && X > NX - 2) return;
   auto W = [&](int j) -> int { return j <= NX - 1 ? R[(size_t)j * pitch] : R[(size_t)(NX - 1) * pitch + (NY - 1)]; };
   const int r0 = W(X);
   const bool neg = r0 < 0;
   int best = r0 * r0;
-  for (int t = 1;; ++t) {
-    const int tt = t * t;
-    if (tt >= best) break;
+  for (int t0 = 1; t0 * t0 < best; t0 += 32) {
+    const int t = t0 + lane, tt = t * t;
     const bool lo_ok = X - t >= 1, hi_ok = X + t <= NX;
-    if (!lo_ok && !hi_ok) break;
-    if (lo_ok) { const int r = W(X - t); best = min(best, tt + (((r < 0) == neg) ? r * r : 0)); }
-    if (hi_ok) { const int r = W(X + t); best = min(best, tt + (((r < 0) == neg) ? r * r : 0)); }
+    int loc = 0x7fffffff;
+    if (lo_ok) { const int r = W(X - t); loc = min(loc, tt + (((r < 0) == neg) ? r * r : 0)); }
+    if (hi_ok) { const int r = W(X + t); loc = min(loc, tt + (((r < 0) == neg) ? r * r : 0)); }
+    best = min(best, __reduce_min_sync(0xffffffffu, loc));
+    if (!__any_sync(0xffffffffu, lo_ok || hi_ok)) break;
   }
+  if (lane) return;
   if (SQ) {
     const int v = best >= SQ_SENT ? ALORE_SQ_INF : best;
     pos_sq[(size_t)X * NY] = neg ? 0 : v;
@@ -1082,6 +1097,28 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
   }
   const int pitch = ((NY + TY - 1) / TY) * TY;
   const int nblk = (NX + BLK - 1) / BLK;
+  // far-cell masks of the superband envelope kernel (K2e): one word per (32-row band, column), rewritten by every K2
+  uint32_t* far_mask = nullptr;
+  if (!getenv("ALORE_ESDF_DC") && !getenv("ALORE_ESDF_NO_BAND")) {
+    // far rows, the Occupied ones among them, one flag per K2 tile, one per tile column
+    const size_t need = ((size_t)(4 * ((NX + TX - 1) / TX)) * pitch + (size_t)((NX + TX - 1) / TX + 1) * ((NY + TY - 1) / TY)) * sizeof(uint32_t);
+    if (need > ctx->band_cap) {
+      if (ctx->d_band) { cudaDeviceSynchronize(); cudaFree(ctx->d_band); }
+      ctx->d_band = nullptr; ctx->band_cap = 0;
+      ALORE_CUDA(ctx, cudaMalloc(&ctx->d_band, need));
+      ALORE_CUDA(ctx, cudaMemset(ctx->d_band, 0, need));          // flags compare against a per-run epoch >= 1
+      ctx->band_cap = need;
+      ctx->band_epoch = 0;
+    }
+    far_mask = static_cast<uint32_t*>(ctx->d_band);
+  }
+  const int epoch = far_mask ? ++ctx->band_epoch : 0;
+  const int ncol_tiles = (NY + TY - 1) / TY;
+  const int* colflag = far_mask ? reinterpret_cast<const int*>(far_mask + (size_t)4 * ((NX + TX - 1) / TX) * pitch) + (size_t)((NX + TX - 1) / TX) * ncol_tiles : nullptr;
+  auto launch_block_min = [&](bool after_k2) {
+    esdf_block_min<<<dim3((pitch / 8 + 31) / 32, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch, after_k2 ? colflag : nullptr, ncol_tiles, epoch);
+  };
+
   if (!sq) {
     const size_t need_row = (size_t)NX * pitch, need_blk = (size_t)(nblk + (nblk + SBLK - 1) / SBLK) * pitch;
     if (need_row > ctx->row_cap) {
@@ -1117,12 +1154,15 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     else
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     if (ref_compat && NX >= 3 && NY >= 2) ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // the aliased column forks here
-    esdf_block_min<<<dim3((pitch / 8 + 31) / 32, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch);
-    if (nblk > SB_MIN_BLOCKS) {
-      esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
+    ctx->launches++;
+    if (!far_mask) {                                   // search path (ALORE_ESDF_NO_BAND / _DC): K2 itself prunes with the minima
+      launch_block_min(false);
       ctx->launches++;
+      if (nblk > SB_MIN_BLOCKS) {
+        esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
+        ctx->launches++;
+      }
     }
-    ctx->launches += 2;
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
     return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
   }
@@ -1141,18 +1181,6 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_col_dc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem));
     ALORE_CUDA(ctx, cudaFuncSetAttribute(esdf_col_dc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem));
   }
-  // far-cell masks of the superband envelope kernel (K2e): one word per (32-row band, column), rewritten by every K2
-  uint32_t* far_mask = nullptr;
-  if (!use_dc && !getenv("ALORE_ESDF_NO_BAND")) {
-    const size_t need = ((size_t)(4 * ((NX + TX - 1) / TX)) * pitch + (size_t)((NX + TX - 1) / TX) * ((NY + TY - 1) / TY)) * sizeof(uint32_t);   // far rows, the Occupied ones among them, one flag per K2 tile
-    if (need > ctx->band_cap) {
-      if (ctx->d_band) { cudaDeviceSynchronize(); cudaFree(ctx->d_band); }
-      ctx->d_band = nullptr; ctx->band_cap = 0;
-      ALORE_CUDA(ctx, cudaMalloc(&ctx->d_band, need));
-      ctx->band_cap = need;
-    }
-    far_mask = static_cast<uint32_t*>(ctx->d_band);
-  }
   // superband height: tall bands amortise the candidate scan (O(reach + band) per thread), short ones give more threads
   int band_nj = (size_t)NX * NY < ((size_t)8 << 20) ? 1 : 2;          // measured: 32 rows on 2048^2 (more threads), 64 on 16 Mcells
   if (const char* e = getenv("ALORE_ESDF_SB")) { const int v = atoi(e); band_nj = v >= 256 ? 8 : (v >= 128 ? 4 : (v >= 64 ? 2 : 1)); }
@@ -1164,16 +1192,17 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     else
     {
       esdf_col_pass<true><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
-                                                g.grid_interval, ref_compat, d_pos_sq, d_neg_sq, far_mask);
+                                                g.grid_interval, ref_compat, d_pos_sq, d_neg_sq, far_mask, epoch);
+      if (far_mask) { launch_block_min(true); ctx->launches++; }
       if (far_mask) {
         switch (band_nj) {
-          case 8: esdf_band_kernel<true, 8><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          case 8: esdf_band_kernel<true, 8><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                           min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
-          case 4: esdf_band_kernel<true, 4><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          case 4: esdf_band_kernel<true, 4><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                           min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
-          case 2: esdf_band_kernel<true, 2><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          case 2: esdf_band_kernel<true, 2><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                           min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
-          default: esdf_band_kernel<true, 1><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          default: esdf_band_kernel<true, 1><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                           min_x, min_y, g.grid_interval, d_pos_sq, d_neg_sq); break;
         }
         ctx->launches++;
@@ -1181,7 +1210,7 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     }
     ctx->launches++;
     if (quirk) {
-      esdf_quirk_col<true><<<(NX + 127) / 128, 128, 0, st>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+      esdf_quirk_col<true><<<(NX + 7) / 8, 256, 0, st>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
                                                              g.grid_interval, d_pos_sq, d_neg_sq);
       ctx->launches++;
     }
@@ -1190,7 +1219,7 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     const bool side = quirk && NX >= 3;
     if (side) {
       ALORE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-      esdf_quirk_col<false><<<(NX + 127) / 128, 128, 0, ctx->stream2>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
+      esdf_quirk_col<false><<<(NX + 7) / 8, 256, 0, ctx->stream2>>>(ctx->d_row, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
                                                                        g.grid_interval, nullptr, nullptr);
       ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
       ctx->launches++;
@@ -1201,16 +1230,17 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     else
     {
       esdf_col_pass<false><<<grid, 256, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, d_dist, g.gly, min_x, min_y,
-                                                 g.grid_interval, ref_compat, nullptr, nullptr, far_mask);
+                                                 g.grid_interval, ref_compat, nullptr, nullptr, far_mask, epoch);
+      if (far_mask) { launch_block_min(true); ctx->launches++; }
       if (far_mask) {
         switch (band_nj) {
-          case 8: esdf_band_kernel<false, 8><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          case 8: esdf_band_kernel<false, 8><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                            min_x, min_y, g.grid_interval, nullptr, nullptr); break;
-          case 4: esdf_band_kernel<false, 4><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          case 4: esdf_band_kernel<false, 4><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                            min_x, min_y, g.grid_interval, nullptr, nullptr); break;
-          case 2: esdf_band_kernel<false, 2><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          case 2: esdf_band_kernel<false, 2><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                            min_x, min_y, g.grid_interval, nullptr, nullptr); break;
-          default: esdf_band_kernel<false, 1><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), d_dist, g.gly,
+          default: esdf_band_kernel<false, 1><<<band_grid, 128, 0, st>>>(ctx->d_row, pitch, ctx->d_blk, pitch, NX, NY, far_mask, pitch, 2 * ((NX + TX - 1) / TX), epoch, d_dist, g.gly,
                                                            min_x, min_y, g.grid_interval, nullptr, nullptr); break;
         }
         ctx->launches++;
