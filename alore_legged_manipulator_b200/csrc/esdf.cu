@@ -842,11 +842,18 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
   // search almost converged (large empty / solid regions).  Any valid upper bound keeps the search exact.
   int prev_best = -1, prev_r = -2;
   bool prev_neg = false;
+  // A thread's cells sit next to each other in the list and share ONE shared-memory bank (same column, row stride of
+  // 64 words): the lanes of a warp walk the list 33 entries apart (odd multiplier modulo a power of two: a bijection),
+  // i.e. in different columns.
+  int lmod = 256;
+  while (lmod < ndef) lmod <<= 1;
   for (int idx = threadIdx.x;; idx += 256) {
     int th, r;
     bool own = false;
-    if (idx < ndef) {
-      const unsigned e = s_list[idx];
+    if (idx < lmod) {
+      const int slot = (idx * 33) & (lmod - 1);
+      if (slot >= ndef) continue;
+      const unsigned e = s_list[slot];
       if ((e >> 5) >= 256) continue;                                  // slot reserved by a thread that did not fit
       th = e >> 5; r = e & 31;
     } else if (defer) {
