@@ -175,6 +175,8 @@ __device__ __forceinline__ void excl_scan4(int& a, int& b, int& c, int& d, int (
   }
   if (lane == 31) { s_agg[0][w] = ia; s_agg[1][w] = ib; }
   if (lane == 0) { s_agg[2][w] = ic; s_agg[3][w] = id; }
+  if (w == 0 && (lane & 7) >= (int)(blockDim.x >> 5))                // CTAs of fewer than 8 warps (short rows): identities
+    s_agg[lane >> 3][lane & 7] = (lane >> 3) < 2 ? identMax : identMin;
   // exclusive within the warp
   int ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
   int ec = __shfl_down_sync(0xffffffffu, ic, 1), ed = __shfl_down_sync(0xffffffffu, id, 1);
@@ -291,12 +293,34 @@ esdf_row_pass16(const uint8_t* __restrict__ occ, size_t occ_total, int gly, int 
       int16_t* dst = R + (size_t)X * pitch + y0;
       reinterpret_cast<uint4*>(dst)[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
       reinterpret_cast<uint4*>(dst)[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
-      for (unsigned m = om[q]; m; m &= m - 1) {
-        const int i = __ffs(m) - 1;
-        const unsigned fl = fm[q] & ((1u << i) - 1u), fr = fm[q] >> (i + 1);
-        const int dl = fl ? i - (31 - __clz(fl)) : (y0 + i) - lf;      // lf = -BIG when the row has no free cell to the left
-        const int dr = fr ? __ffs(fr) : rf[q] - (y0 + i);              // rf = BIG when none to the right
-        dst[i] = (int16_t)(-min(min(dl, dr), SENT));
+      if (__popc(om[q]) <= 3) {                       // cluttered maps: a few bit scans
+        for (unsigned m = om[q]; m; m &= m - 1) {
+          const int i = __ffs(m) - 1;
+          const unsigned fl = fm[q] & ((1u << i) - 1u), fr = fm[q] >> (i + 1);
+          const int dl = fl ? i - (31 - __clz(fl)) : (y0 + i) - lf;      // lf = -BIG when the row has no free cell to the left
+          const int dr = fr ? __ffs(fr) : rf[q] - (y0 + i);              // rf = BIG when none to the right
+          dst[i] = (int16_t)(-min(min(dl, dr), SENT));
+        }
+      } else {                                        // solid regions: the same two recurrences, towards the nearest FREE cell
+        int dl_f[16];
+        int ef = min(y0 - 1 - lf, 2 * SENT);          // distance of cell -1 to the nearest free cell on its left
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          ef = ((fm[q] >> i) & 1u) ? 0 : ef + 1;
+          dl_f[i] = ef;
+        }
+        ef = min(rf[q] - (y0 + 16), 2 * SENT);
+#pragma unroll
+        for (int i = 15; i >= 0; i--) {
+          ef = ((fm[q] >> i) & 1u) ? 0 : ef + 1;
+          if ((om[q] >> i) & 1u) {
+            const unsigned v = (unsigned)(-min(min(dl_f[i], ef), SENT)) & 0xffffu;
+            if (i & 1) outw[i >> 1] = (outw[i >> 1] & 0x0000ffffu) | (v << 16);
+            else outw[i >> 1] = (outw[i >> 1] & 0xffff0000u) | v;
+          }
+        }
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
       }
       // carries for the next owned group
       if (om[q]) lo = y0 + 31 - __clz(om[q]);
@@ -1150,8 +1174,8 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     const int GP = (G16 + ROW_THREADS - 1) / ROW_THREADS;
     const bool fast = (((uintptr_t)d_occ & 15) == 0) && (g.gly % 16 == 0) && (min_y % 16 == 0) && GP <= ROW_GP_MAX;
     const size_t occ_total = (size_t)g.glx * g.gly;
-    if (fast && GP <= 1)
-      esdf_row_pass16<1><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
+    if (fast && GP <= 1)                               // one 16-cell group per thread: no idle warps on short rows
+      esdf_row_pass16<1><<<NX, std::min(ROW_THREADS, ((G16 + 31) / 32) * 32), 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     else if (fast && GP <= 2)
       esdf_row_pass16<2><<<NX, ROW_THREADS, 0, st>>>(d_occ, occ_total, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     else if (fast && GP <= 4)
