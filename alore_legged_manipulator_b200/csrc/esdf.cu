@@ -546,6 +546,12 @@ __device__ __forceinline__ int esdf_band_bound(const uint32_t* __restrict__ blkc
   return (int)U;
 }
 
+#ifdef ALORE_BAND_STATS
+__device__ unsigned long long g_band_dbg[8];   // developer counters: blocks seen / needed, rows seen / past the filter / stored, items
+#define BAND_STAT(i, v) atomicAdd(&g_band_dbg[i], (unsigned long long)(v))
+#else
+#define BAND_STAT(i, v)
+#endif
 template <bool SQ, int ENV_NJ>
 __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, int pitch, const uint32_t* __restrict__ blk, int blk_pitch,
                                                 int NX, int NY, const uint32_t* __restrict__ fm, int mpitch, int nbands, int j0, int j1,
@@ -578,8 +584,7 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
   cl = max(cl, 0); ch = min(ch, NX - 1);
   // 2. the stack of the candidate rows, ascending; top two sites in registers.  All products are integers below 2^53,
   //    so the tests are done in FP64 (exact) — one DMUL where the integer pipe needs four IMADs.
-  int sv[ENV_CAP];
-  unsigned sf[ENV_CAP];
+  unsigned long long stk[ENV_CAP];               // site: row x in the high word, f = g^2 + x^2 in the low word
   int top = -1;
   double vt = 0.0, vp = 0.0, ft = 0.0, fp = 0.0;
   bool overflow = false;
@@ -588,10 +593,13 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
 #pragma unroll
   for (int j = 0; j < ENV_NJ; j++)
     if (j < j1 - j0 && Uj[j] >= 0) Umax = max(Umax, (unsigned)Uj[j]);
+  const int pad = neg ? -SENT : SENT;
+  const size_t rstride = (size_t)pitch;
   for (int b = cl / BLK; b <= ch / BLK && !overflow; b++) {
     const int b0 = b * BLK, b1 = min(b0 + BLK - 1, NX - 1);
     const uint32_t mm = blkc[(size_t)b * blk_pitch];
     const int m = neg ? (int)(mm >> 16) : (int)(mm & 0xffffu);
+    BAND_STAT(0, 1);
     if (m >= SENT) continue;
     bool need = false;
     for (int j = 0; j < j1 - j0 && !need; j++) {
@@ -600,39 +608,46 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
       need = (long long)dn * dn + (long long)m * m <= (long long)Uj[j];
     }
     if (!need) continue;
+    BAND_STAT(1, 1);
+    const int16_t* rp = Rc + (size_t)b0 * rstride;          // walks down the column, 8 rows in flight
     int rr[8], rn[8];
-    const int pad = neg ? -SENT : SENT;
 #pragma unroll
-    for (int i = 0; i < 8; i++) rr[i] = (b0 + i <= b1) ? (int)Rc[(size_t)(b0 + i) * pitch] : pad;
+    for (int i = 0; i < 8; i++) rr[i] = (b0 + i <= b1) ? (int)rp[i * rstride] : pad;
 #pragma unroll 1
     for (int xb = b0; xb <= b1; xb += 8) {
+      rp += 8 * rstride;
 #pragma unroll
-      for (int i = 0; i < 8; i++) rn[i] = (xb + 8 + i <= b1) ? (int)Rc[(size_t)(xb + 8 + i) * pitch] : pad;   // next batch in flight
+      for (int i = 0; i < 8; i++) rn[i] = (xb + 8 + i <= b1) ? (int)rp[i * rstride] : pad;   // next batch in flight
+      const double xbd = (double)xb;
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int x = xb + i;
         const int g = neg ? max(-rr[i], 0) : max(rr[i], 0);    // a row of the other kind is a seed itself
         const int dnr = max(max(lo - x, x - hi), 0);
         // no seed of this kind in the row, or a site that cannot reach any far row of the band: never an owner
+        BAND_STAT(2, 1);
         if (g >= SENT || (unsigned)(dnr * dnr) + (unsigned)(g * g) > Umax) continue;
+        BAND_STAT(3, 1);
         const unsigned fi = (unsigned)(g * g) + (unsigned)(x * x);
-        const double f = (double)fi, xd = (double)x;
+        const double f = (double)fi, xd = xbd + (double)i;
         double bx = xd - vt, cf = f - ft;
         while (top >= 1 && (ft - fp) * bx >= cf * (vt - vp)) {
           top--;
           vt = vp; ft = fp;
-          if (top >= 1) { vp = (double)sv[top - 1]; fp = (double)sf[top - 1]; }
+          if (top >= 1) { const unsigned long long e = stk[top - 1]; vp = (double)(int)(e >> 32); fp = (double)(unsigned)e; }
           bx = xd - vt; cf = f - ft;
         }
         if (top >= 0 && cf >= hi2 * bx) continue;              // loses to the top at X = hi
+        const unsigned long long site = ((unsigned long long)(unsigned)x << 32) | fi;
         if (top == 0 && cf < lo2 * bx) {                         // the only site loses the whole band
-          sv[0] = x; sf[0] = fi;
+          stk[0] = site;
           vt = xd; ft = f;
           continue;
         }
         if (top + 1 >= ENV_CAP) { overflow = true; break; }
+        BAND_STAT(4, 1);
         ++top;
-        sv[top] = x; sf[top] = fi;
+        stk[top] = site;
         vp = vt; fp = ft; vt = xd; ft = f;
       }
 #pragma unroll
@@ -641,11 +656,14 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
     }
   }
   if (overflow) return false;
+  BAND_STAT(5, 1);
+  BAND_STAT(6, hi - lo + 1);
+  BAND_STAT(7, ch - cl + 1);
   // 3. the far rows of this kind, ascending, pointer walk
   int k = 0;
   double vk = 0.0, fk = 0.0, vn = 0.0, fn = 0.0;
-  if (top >= 0) { vk = (double)sv[0]; fk = (double)sf[0]; }
-  if (top >= 1) { vn = (double)sv[1]; fn = (double)sf[1]; }
+  if (top >= 0) { vk = (double)(int)(stk[0] >> 32); fk = (double)(unsigned)stk[0]; }
+  if (top >= 1) { vn = (double)(int)(stk[1] >> 32); fn = (double)(unsigned)stk[1]; }
   for (int j = j0; j < j1; j++) {
     unsigned mk = rows_of(j);
     while (mk) {
@@ -660,7 +678,7 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
           if (cn > ck) break;
           ck = cn; k++;
           vk = vn; fk = fn;
-          if (k < top) { vn = (double)sv[k + 1]; fn = (double)sf[k + 1]; }
+          if (k < top) { const unsigned long long e = stk[k + 1]; vn = (double)(int)(e >> 32); fn = (double)(unsigned)e; }
         }
         const double v = ck + (double)X * (double)X;
         best = v < (double)SQ_SENT ? (int)v : SQ_SENT;
@@ -1281,5 +1299,15 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
     if (side) ALORE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
   }
   ALORE_CUDA(ctx, cudaGetLastError());
+#ifdef ALORE_BAND_STATS
+  {
+    cudaDeviceSynchronize();
+    unsigned long long h[8], z[8] = {0};
+    cudaMemcpyFromSymbol(h, g_band_dbg, sizeof(h));
+    cudaMemcpyToSymbol(g_band_dbg, z, sizeof(z));
+    fprintf(stderr, "[band] blocks seen %llu needed %llu | rows seen %llu past filter %llu stored %llu | items %llu band rows %llu range rows %llu\n",
+            h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+  }
+#endif
   return ALORE_OK;
 }
