@@ -83,6 +83,33 @@ def test_esdf_divide_and_conquer_column_pass_bit_exact(shape):
     ctx.close()
 
 
+@pytest.mark.parametrize("knobs", [dict(ALORE_ESDF_NO_BAND=1), dict(ALORE_ESDF_SB=32), dict(ALORE_ESDF_SB=64),
+                                   dict(ALORE_ESDF_SB=128), dict(ALORE_ESDF_SB=256)])
+def test_esdf_far_field_paths_bit_exact(knobs):
+    """Far cells (large empty / solid regions): the band lower-envelope kernel at every band height and the round-1
+    per-cell search must all reproduce the oracle bit for bit, on maps that are nearly empty, nearly solid and mixed."""
+    import alore_legged_manipulator_b200 as alore
+    ctx = alore.Context(0)
+    for (glx, gly), seed, kw in (((700, 300), 2, dict(p_occ=0.0, p_unknown=0.0, boxes=5, box_cells=(4, 40))),
+                                 ((513, 257), 3, dict(p_occ=0.0, p_unknown=0.0, wall=False, boxes=1, box_cells=(2, 3))),
+                                 ((300, 900), 4, dict(p_occ=0.0, p_unknown=0.0, boxes=30, box_cells=(40, 200))),
+                                 ((1100, 260), 5, dict(p_occ=1.0, p_unknown=0.0))):
+        grid = workloads.random_map(glx, gly, seed, **kw)
+        if kw.get("p_occ") == 1.0:                           # a solid world with one free pocket and one free cell
+            g2 = grid.reshape(glx, gly)
+            g2[500:520, 100:130] = workloads.UNOCCUPIED
+            g2[40, 200] = workloads.UNOCCUPIED
+        m = make_sdf(ctx, glx, gly, 0.05, grid)
+        with env(**knobs):
+            m.updateESDF2d()
+        ref = np.full(glx * gly, np.finfo(np.float64).max)
+        mn, mx = m.esdf_window()
+        oracle_lib.esdf_update(m.geom(), grid, mn, mx, ref)
+        assert np.array_equal(m.distance_buffer_all_.view(np.uint64), ref.view(np.uint64)), ((glx, gly), seed, knobs)
+        m.close()
+    ctx.close()
+
+
 @pytest.mark.parametrize("shape", [32, 128, 640, 641, 1281])
 def test_penalty_kernel_shapes_bit_identical(world, portable_trig, shape):
     m, prm, pl, grid = world
