@@ -520,26 +520,38 @@ __device__ __forceinline__ int esdf_band_bound(const uint32_t* __restrict__ blkc
       U = min(U, (long long)df * df + (long long)m * m);
     }
   }
-  for (int d = 1;; d++) {
-    const int ba = bL - d, bb = bH + d;
-    bool any = false;
-    if (ba >= 0) {
-      const int b0 = ba * BLK, b1 = b0 + BLK - 1;
-      const int dn = lo - b1;
-      if ((long long)dn * dn < U) {
-        any = true;
-        const int m = mg(ba);
-        if (m < SENT) { const int df = hi - b0; U = min(U, (long long)df * df + (long long)m * m); }
-      }
+  // outwards, four blocks per side in flight (the minima are the only loads of this loop; reading a few blocks
+  // past the last useful one is harmless)
+  for (int d0 = 1;; d0 += 4) {
+    int ma[4], mb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int ba = bL - d0 - i, bb = bH + d0 + i;
+      ma[i] = ba >= 0 ? mg(ba) : SENT;
+      mb[i] = bb < nblk ? mg(bb) : SENT;
     }
-    if (bb < nblk) {
-      const int b0 = bb * BLK, b1 = min(b0 + BLK - 1, NX - 1);
-      const int dn = b0 - hi;
-      if ((long long)dn * dn < U) {
-        any = true;
-        const int m = mg(bb);
-        if (m < SENT) { const int df = b1 - lo; U = min(U, (long long)df * df + (long long)m * m); }
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int ba = bL - d0 - i, bb = bH + d0 + i;
+      any = false;
+      if (ba >= 0) {
+        const int b0 = ba * BLK, b1 = b0 + BLK - 1;
+        const int dn = lo - b1;
+        if ((long long)dn * dn < U) {
+          any = true;
+          if (ma[i] < SENT) { const int df = hi - b0; U = min(U, (long long)df * df + (long long)ma[i] * ma[i]); }
+        }
       }
+      if (bb < nblk) {
+        const int b0 = bb * BLK, b1 = min(b0 + BLK - 1, NX - 1);
+        const int dn = b0 - hi;
+        if ((long long)dn * dn < U) {
+          any = true;
+          if (mb[i] < SENT) { const int df = b1 - lo; U = min(U, (long long)df * df + (long long)mb[i] * mb[i]); }
+        }
+      }
+      if (!any) break;
     }
     if (!any) break;
   }
@@ -595,9 +607,17 @@ __device__ __noinline__ bool esdf_band_envelope(const int16_t* __restrict__ R, i
     if (j < j1 - j0 && Uj[j] >= 0) Umax = max(Umax, (unsigned)Uj[j]);
   const int pad = neg ? -SENT : SENT;
   const size_t rstride = (size_t)pitch;
-  for (int b = cl / BLK; b <= ch / BLK && !overflow; b++) {
+  const int bfirst = cl / BLK, blast = ch / BLK;
+  uint32_t mq[8];                                  // block minima, eight blocks in flight
+  for (int b = bfirst; b <= blast && !overflow; b++) {
+    if (((b - bfirst) & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) mq[i] = blkc[(size_t)min(b + i, blast) * blk_pitch];
+    }
+    uint32_t mm = mq[0];
+#pragma unroll
+    for (int i = 0; i < 7; i++) mq[i] = mq[i + 1];
     const int b0 = b * BLK, b1 = min(b0 + BLK - 1, NX - 1);
-    const uint32_t mm = blkc[(size_t)b * blk_pitch];
     const int m = neg ? (int)(mm >> 16) : (int)(mm & 0xffffu);
     BAND_STAT(0, 1);
     if (m >= SENT) continue;
