@@ -166,6 +166,10 @@ __device__ __forceinline__ int next_job(int* counter, int lane) {
 #ifndef ALORE_OPT_MINBLOCKS
 #define ALORE_OPT_MINBLOCKS 8
 #endif
+#ifdef ALORE_CAND_TIMING   // developer build: wall time of every candidate inside the persistent kernel (scripts/cand_timing.py)
+__device__ unsigned long long g_cand_ns[3 * 16384];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
 __global__ void __launch_bounds__(32, ALORE_OPT_MINBLOCKS)
 opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, double* slabs, double* hists, int* counter) {
   extern __shared__ __align__(16) double smem[];
@@ -186,7 +190,17 @@ opt_kernel(const __grid_constant__ KParams kp, BatchDev bt, ResultDev out, doubl
     const int N = bt.piece_off[b + 1] - bt.piece_off[b];
     Warp w;
     carve(w, kp.L, smem, slab, hist, N, kp.P.sparseResolution);
+#ifdef ALORE_CAND_TIMING
+    const unsigned long long t0 = gtimer();
+#endif
     minco_plan(w, kp, bt, b, out);
+#ifdef ALORE_CAND_TIMING
+    if (lane == 0 && b < 16384) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      g_cand_ns[3 * b] = t0; g_cand_ns[3 * b + 1] = gtimer(); g_cand_ns[3 * b + 2] = smid;
+    }
+#endif
   }
 }
 
@@ -854,6 +868,14 @@ int alore_batch_run(alore_ctx* ctx, const alore_params_t* prm, alore_batch* bh, 
     ALORE_CUDA(ctx, cudaGetLastError());
     ALORE_CUDA(ctx, cudaEventRecord(bh->e1, st));
     ctx->last_batch = bh;
+#ifdef ALORE_CAND_TIMING
+    if (const char* f = getenv("ALORE_CAND_TIMING_DUMP")) {
+      cudaDeviceSynchronize();
+      std::vector<unsigned long long> h(3 * 16384);
+      cudaMemcpyFromSymbol(h.data(), g_cand_ns, h.size() * sizeof(unsigned long long));
+      if (FILE* fp = fopen(f, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), fp); fclose(fp); }
+    }
+#endif
     return ALORE_OK;
   }
   bh->runs++;
