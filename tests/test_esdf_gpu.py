@@ -121,3 +121,41 @@ def test_config5_shape_8192x2048_bit_exact(ctx):
     glx, gly = 8192, 2048
     grid = workloads.corridor_map(glx, gly, 5, width_cells=400, clutter=0.02)
     check_against_oracle(ctx, glx, gly, 0.005, grid, check_sq=False)
+
+
+def patchwork_map(glx, gly, rng):
+    """Rectangles of very different character side by side: solid, empty, cluttered, sparse seeds, unknown."""
+    g = np.full((glx, gly), capi.UNOCCUPIED, dtype=np.uint8)
+    for _ in range(int(rng.integers(3, 9))):
+        w, h = int(rng.integers(8, max(9, glx // 2))), int(rng.integers(8, max(9, gly // 2)))
+        x0, y0 = int(rng.integers(0, max(1, glx - w))), int(rng.integers(0, max(1, gly - h)))
+        kind = int(rng.integers(0, 5))
+        blk = g[x0:x0 + w, y0:y0 + h]
+        if kind == 0:
+            blk[:] = capi.OCCUPIED
+        elif kind == 1:
+            blk[:] = capi.UNOCCUPIED
+        elif kind == 2:
+            blk[rng.random(blk.shape) < 0.05] = capi.OCCUPIED
+        elif kind == 3:
+            blk[rng.random(blk.shape) < 0.6] = capi.OCCUPIED
+        else:
+            blk[:] = capi.UNKNOWN
+    if rng.random() < 0.3:
+        g[int(rng.integers(0, glx)), int(rng.integers(0, gly))] = capi.OCCUPIED
+    return np.ascontiguousarray(g.reshape(-1))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_patchwork_maps_and_windows_bit_exact(ctx, seed):
+    """Near-field, far-field and dense regions in ONE map (every hand-over between K2, the deferred list and the band
+    kernel inside a single tile), odd sizes, windows that start and end anywhere; distances and both squared planes."""
+    rng = np.random.default_rng(1234 + seed)
+    glx, gly = int(rng.integers(40, 700)), int(rng.integers(40, 700))
+    grid = patchwork_map(glx, gly, rng)
+    gi = 0.1
+    if seed % 3 == 0:                                  # full map
+        check_against_oracle(ctx, glx, gly, gi, grid)
+    else:                                              # a window around a random odometry position
+        odom = (float(rng.uniform(-0.4, 0.4) * glx * gi), float(rng.uniform(-0.4, 0.4) * gly * gi))
+        check_against_oracle(ctx, glx, gly, gi, grid, odom=odom, rng_m=float(rng.uniform(2.0, 0.45 * min(glx, gly) * gi)))
