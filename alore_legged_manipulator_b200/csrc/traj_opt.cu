@@ -1047,7 +1047,9 @@ static int penalty_launch(alore_ctx* ctx, const alore_params_t* prm, int B, int 
   kp.Nmax = Nmax; kp.npadmax = (3 * Nmax) & ~1; kp.mcap = 1;
   // threads per trajectory x resident CTAs per SM x placement of the per-sample intermediates (tuning knob
   // ALORE_PEN_SHAPE; default chosen by measurement on configs[2]: 64 threads, 6 CTAs per SM, intermediates in the L2-resident
-  // per-CTA slab — 0.65 ms; 128 threads 0.84, one warp 0.81, shared-memory intermediates 0.77 (8 warps per SM), more CTAs 0.69+)
+  // per-CTA slab — 0.65 ms; 128 threads 0.84, one warp 0.81, shared-memory intermediates 0.77 (8 warps per SM), more CTAs 0.69+,
+  // FEWER CTAs (ALORE_PEN_CTAS_PER_SM = 5 / 4 / 3) 0.71 / 0.80 / 0.98, a persisting-L2 window on the slabs 0.70: the 888 slabs
+  // of 160 KB exceed L2, but the kernel needs the parallelism more than the hit rate)
   int shape = 64;
   if (const char* e = getenv("ALORE_PEN_SHAPE")) shape = atoi(e);
   const size_t smem_on = wave::pen_smem_doubles_onchip(Nmax, prm->sparseResolution) * sizeof(double);
@@ -1059,6 +1061,7 @@ static int penalty_launch(alore_ctx* ctx, const alore_params_t* prm, int B, int 
     int occ = 0;
     ALORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) return alore_fail(ctx, ALORE_EINVAL, "kernel does not fit on an SM");
+    if (const char* e = getenv("ALORE_PEN_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1) occ = std::min(occ, v); }   // tuning knob
     const int grid = std::max(1, std::min(B, occ * ctx->sm_count));
     const size_t need = (size_t)grid * kp.L.total * sizeof(double);
     if (need > ctx->opt_scratch_bytes) {
