@@ -489,6 +489,10 @@ __device__ __forceinline__ double esdf_value(int best, bool neg, double gi) {
 // random columns, ties included); the stack never held more than (hi - lo + 1) + 2 sites.  The top two sites live in
 // registers: a row costs no dependent memory access unless it pops.  The far rows are then answered by a pointer walk
 // (owners are monotone).  O(candidate rows + band rows) per (superband, column).
+// K2e hand-over buffer: [BAND_FLAG_WORDS flags][far-row masks][Occupied masks].  The flags sit at a FIXED place in front of
+// the geometry-dependent mask planes, so a word that was a mask under another window shape can never be read as a flag;
+// a flag is "set" when it holds the current run's epoch (never cleared, stale values are always older).
+constexpr int BAND_FLAG_WORDS = 33024;          // (16384/64) x (16384/128) tiles + 128 tile columns, 256-byte multiple
 constexpr int ENV_CAP = 512;                    // stack capacity; (rows of the superband) + 2 is what the band can need
 // rows per superband = 32 * ENV_NJ (template parameter: 2, 4 or 8 sub-bands; chosen by the host from the window size)
 template <bool SQ>
@@ -721,7 +725,7 @@ esdf_band_kernel(const int16_t* __restrict__ R, int pitch, const uint32_t* __res
   const uint32_t* fm = far_mask + y;
   const int j0 = blockIdx.y * ENV_NJ, j1 = min(j0 + ENV_NJ, (NX + 31) / 32);
   // tiles of K2 (64 rows x 128 columns) that left nothing this run (flag != epoch): their masks are not even written
-  const int* flag = reinterpret_cast<const int*>(far_mask + (size_t)2 * nbands * mpitch) + blockIdx.x;
+  const int* flag = reinterpret_cast<const int*>(far_mask) - BAND_FLAG_WORDS + blockIdx.x;
   unsigned live = 0u;
 #pragma unroll
   for (int i = 0; i < ENV_NJ; i++)
@@ -982,8 +986,8 @@ esdf_col_pass(const int16_t* __restrict__ R, int pitch, const uint32_t* __restri
       far_mask[(size_t)(blockIdx.y * 2 + half) * pitch + y] = s_far[threadIdx.x];
       far_mask[(size_t)(gridDim.y * 2 + blockIdx.y * 2 + half) * pitch + y] = s_farneg[threadIdx.x];
     }
-    if (anyfar && threadIdx.x == 0) {                    // flags behind the two mask planes: one per tile, one per tile column;
-      int* flags = reinterpret_cast<int*>(far_mask + (size_t)4 * gridDim.y * pitch);   // "set" = this run's epoch, never cleared
+    if (anyfar && threadIdx.x == 0) {                    // flags in front of the mask planes: one per tile, one per tile column;
+      int* flags = reinterpret_cast<int*>(far_mask) - BAND_FLAG_WORDS;                 // "set" = this run's epoch, never cleared
       flags[blockIdx.y * gridDim.x + blockIdx.x] = epoch;
       flags[gridDim.y * gridDim.x + blockIdx.x] = epoch;
     }
@@ -1169,8 +1173,8 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
   // far-cell masks of the superband envelope kernel (K2e): one word per (32-row band, column), rewritten by every K2
   uint32_t* far_mask = nullptr;
   if (!getenv("ALORE_ESDF_DC") && !getenv("ALORE_ESDF_NO_BAND")) {
-    // far rows, the Occupied ones among them, one flag per K2 tile, one per tile column
-    const size_t need = ((size_t)(4 * ((NX + TX - 1) / TX)) * pitch + (size_t)((NX + TX - 1) / TX + 1) * ((NY + TY - 1) / TY)) * sizeof(uint32_t);
+    // flags (fixed size, in front), then per (32-row band, column) the far rows and the Occupied ones among them
+    const size_t need = ((size_t)BAND_FLAG_WORDS + (size_t)(4 * ((NX + TX - 1) / TX)) * pitch) * sizeof(uint32_t);
     if (need > ctx->band_cap) {
       if (ctx->d_band) { cudaDeviceSynchronize(); cudaFree(ctx->d_band); }
       ctx->d_band = nullptr; ctx->band_cap = 0;
@@ -1179,11 +1183,11 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
       ctx->band_cap = need;
       ctx->band_epoch = 0;
     }
-    far_mask = static_cast<uint32_t*>(ctx->d_band);
+    far_mask = static_cast<uint32_t*>(ctx->d_band) + BAND_FLAG_WORDS;
   }
   const int epoch = far_mask ? ++ctx->band_epoch : 0;
   const int ncol_tiles = (NY + TY - 1) / TY;
-  const int* colflag = far_mask ? reinterpret_cast<const int*>(far_mask + (size_t)4 * ((NX + TX - 1) / TX) * pitch) + (size_t)((NX + TX - 1) / TX) * ncol_tiles : nullptr;
+  const int* colflag = far_mask ? reinterpret_cast<const int*>(far_mask) - BAND_FLAG_WORDS + (size_t)((NX + TX - 1) / TX) * ncol_tiles : nullptr;
   auto launch_block_min = [&](bool after_k2) {
     esdf_block_min<<<dim3((pitch / 8 + 31) / 32, nblk), 128, 0, st>>>(ctx->d_row, pitch, NX, NY, ctx->d_blk, pitch, after_k2 ? colflag : nullptr, ncol_tiles, epoch);
   };
@@ -1194,6 +1198,9 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
       if (ctx->d_row) cudaFree(ctx->d_row);
       ctx->d_row = nullptr;
       ALORE_CUDA(ctx, cudaMalloc(&ctx->d_row, need_row * sizeof(int16_t)));
+      // columns NY..pitch-1 are never written by the row pass but travel through K2's 16-byte tile loads (no output
+      // depends on them): defined once, as "far from any seed"
+      ALORE_CUDA(ctx, cudaMemset(ctx->d_row, 0x7f, need_row * sizeof(int16_t)));
       ctx->row_cap = need_row;
     }
     if (need_blk > ctx->blk_cap) {

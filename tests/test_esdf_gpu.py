@@ -159,3 +159,47 @@ def test_patchwork_maps_and_windows_bit_exact(ctx, seed):
     else:                                              # a window around a random odometry position
         odom = (float(rng.uniform(-0.4, 0.4) * glx * gi), float(rng.uniform(-0.4, 0.4) * gly * gi))
         check_against_oracle(ctx, glx, gly, gi, grid, odom=odom, rng_m=float(rng.uniform(2.0, 0.45 * min(glx, gly) * gi)))
+
+
+def test_stale_handover_words_of_another_window_shape_are_never_read_as_flags():
+    """K2 hands far cells to K2e through masks and per-tile flags kept in a per-context buffer; a flag is "set" when it
+    holds the update's epoch.  Regression: with the flags BEHIND the (shape-dependent) mask planes, a mask word of an
+    earlier, larger window could sit where a later window looks for a flag — and equal its epoch.  Window A (35 rows:
+    the last band has 3 rows, every cell far from the only seed) leaves mask words of value 0b11; window B (two 64x128
+    tiles, cluttered: nothing far) is then updated at every epoch from 2 to 12 — epoch 3 met the stale word."""
+    import alore_legged_manipulator_b200 as alore
+    ctx = alore.Context(0)
+    ga = np.full((35, 1024), capi.UNOCCUPIED, np.uint8)
+    ga[0, 0] = capi.OCCUPIED
+    ga = np.ascontiguousarray(ga.reshape(-1))
+    gb = workloads.random_map(100, 120, 5, p_occ=0.08, p_unknown=0.0, wall=False)
+    for it in range(12):                                  # A once (epoch 1), then B at the epochs 2 .. 12
+        glx, gly, grid = (35, 1024, ga) if it == 0 else (100, 120, gb)
+        m = make_sdf(ctx, glx, gly, 0.1, grid)
+        m.updateESDF2d()
+        ref = np.full(glx * gly, DBL_MAX)
+        mn, mx = m.esdf_window()
+        oracle_lib.esdf_update(m.geom(), grid, mn, mx, ref)
+        assert np.array_equal(m.distance_buffer_all_.view(np.uint64), ref.view(np.uint64)), (it, glx, gly)
+        m.close()
+    ctx.close()
+
+
+def test_alternating_window_shapes_on_one_context():
+    """Three window shapes alternate on ONE context for many updates (the hand-over buffer of K2e survives across
+    updates and is re-used under every shape): every update must reproduce the oracle."""
+    import alore_legged_manipulator_b200 as alore
+    ctx = alore.Context(0)
+    rng = np.random.default_rng(99)
+    shapes = [(130, 520), (260, 260), (70, 900)]
+    for it in range(120):
+        glx, gly = shapes[it % len(shapes)]
+        grid = patchwork_map(glx, gly, rng)
+        m = make_sdf(ctx, glx, gly, 0.1, grid)            # takes the context's map over (one context = one map)
+        m.updateESDF2d()
+        ref = np.full(glx * gly, DBL_MAX)
+        mn, mx = m.esdf_window()
+        oracle_lib.esdf_update(m.geom(), grid, mn, mx, ref)
+        assert np.array_equal(m.distance_buffer_all_.view(np.uint64), ref.view(np.uint64)), (it, glx, gly)
+        m.close()
+    ctx.close()
