@@ -12,6 +12,10 @@ from pathlib import Path
 FRAGMENTS = {
     # name: (file relative to planning_ddr_opt, first line, last line, sanity substring expected on the first line)
     "ref_sdf_esdf.inc": ("utils/plan_env/src/sdf_map.cpp", 618, 715, "void SDFmap::updateESDF2d()"),
+    "ref_sdf_index.inc": ("utils/plan_env/src/sdf_map.cpp", 453, 472, "Eigen::Vector2d SDFmap::gridIndex2coordd(const Eigen::Vector2i &index)"),
+    "ref_sdf_vecnum.inc": ("utils/plan_env/src/sdf_map.cpp", 525, 531, "int SDFmap::Index2Vectornum(const int &x, const int &y)"),
+    "ref_sdf_lookup.inc": ("utils/plan_env/src/sdf_map.cpp", 739, 871, "inline double SDFmap::getDistance(const Eigen::Vector2i& id)"),
+    "ref_sdf_isocc.inc": ("utils/plan_env/src/sdf_map.cpp", 942, 948, "bool SDFmap::isOccWithSafeDis(const Eigen::Vector2i &index, const double &safe_dis)"),
     "ref_minco_banded.inc": ("back_end/include/gcopter/minco.hpp", 43, 198, "class BandedSystem"),
     "ref_opt_tmaps.inc": ("back_end/src/optimizer.cpp", 573, 591, "template <typename EIGENVEC>"),
     "ref_opt_smoothl1.inc": ("back_end/src/optimizer.cpp", 1069, 1106, "inline void MSPlanner::positiveSmoothedL1"),

@@ -35,8 +35,28 @@ class SDFmap {
   template <typename F_get_val, typename F_set_val>
   void fillESDF(F_get_val f_get_val, F_set_val f_set_val, int start, int end, int dim_size);
   void publish_ESDF();
+  // the lookup functions of the optimizer's penalty functional and of the collision checks (sdf_map.cpp:453-472, 525-531,
+  // 739-871, 942-948)
+  Eigen::Vector2d gridIndex2coordd(const Eigen::Vector2i& index);
+  Eigen::Vector2d gridIndex2coordd(const int& x, const int& y);
+  Eigen::Vector2i coord2gridIndex(const Eigen::Vector2d& pt);
+  int Index2Vectornum(const int& x, const int& y);
+  int Index2Vectornum(const Eigen::Vector2i& index);
+  inline double getDistance(const Eigen::Vector2i& id);
+  inline double getDistance(const int& idx, const int& idy);
+  inline Eigen::Vector2i ESDFcoord2gridIndex(const Eigen::Vector2d& pt);
+  double getDistWithGradBilinear(const Eigen::Vector2d& pos, Eigen::Vector2d& grad);
+  double getDistWithGradBilinear(const Eigen::Vector2d& pos, Eigen::Vector2d& grad, const double& mindis);
+  double getDistWithGradBilinear(const Eigen::Vector2d& pos);
+  double getDistanceReal(const Eigen::Vector2d& pos);
+  bool isOccWithSafeDis(const Eigen::Vector2i& index, const double& safe_dis);
+  bool isOccWithSafeDis(const int& idx, const int& idy, const double& safe_dis);
 };
 #include "_ref/gen/ref_sdf_esdf.inc"
+#include "_ref/gen/ref_sdf_index.inc"
+#include "_ref/gen/ref_sdf_vecnum.inc"
+#include "_ref/gen/ref_sdf_lookup.inc"
+#include "_ref/gen/ref_sdf_isocc.inc"
 
 // ---- minco::BandedSystem, the whole class --------------------------------------------------------------------------
 namespace minco {
@@ -71,6 +91,33 @@ int ref_esdf_update(const alore_map_geom_t* g, const uint8_t* occ, double odom_x
   m.distance_buffer_all_.assign(dist_inout, dist_inout + n);
   m.updateESDF2d();
   std::memcpy(dist_inout, m.distance_buffer_all_.data(), n * sizeof(double));
+  return 0;
+}
+
+static void ref_map_init(SDFmap& m, const alore_map_geom_t* g, const double* dist) {
+  m.GLX_SIZE_ = g->glx; m.GLY_SIZE_ = g->gly;
+  m.global_x_lower_ = g->x_lower; m.global_y_lower_ = g->y_lower; m.global_x_upper_ = g->x_upper; m.global_y_upper_ = g->y_upper;
+  m.grid_interval_ = g->grid_interval; m.inv_grid_interval_ = g->inv_grid_interval;
+  m.distance_buffer_all_.assign(dist, dist + (size_t)g->glx * g->gly);
+}
+
+// n lookups through the reference's own getDistWithGradBilinear (which = 3: with mindis, 2: with gradient, 1: value
+// only), getDistanceReal (which = 0) and isOccWithSafeDis at coord2gridIndex(pos) (which = -1; out = 0 / 1).
+// grad_io [n][2] is in/out: the reference leaves it untouched on some paths.
+int ref_dist_lookups(const alore_map_geom_t* g, const double* dist, int n, const double* pos, int which, double mindis, double* out,
+                     double* grad_io) {
+  SDFmap m;
+  ref_map_init(m, g, dist);
+  for (int i = 0; i < n; i++) {
+    const Eigen::Vector2d p(pos[2 * i], pos[2 * i + 1]);
+    Eigen::Vector2d gr(grad_io ? grad_io[2 * i] : 0.0, grad_io ? grad_io[2 * i + 1] : 0.0);
+    if (which == 3) out[i] = m.getDistWithGradBilinear(p, gr, mindis);
+    else if (which == 2) out[i] = m.getDistWithGradBilinear(p, gr);
+    else if (which == 1) out[i] = m.getDistWithGradBilinear(p);
+    else if (which == 0) out[i] = m.getDistanceReal(p);
+    else out[i] = m.isOccWithSafeDis(m.coord2gridIndex(p), mindis) ? 1.0 : 0.0;
+    if (grad_io) { grad_io[2 * i] = gr.x(); grad_io[2 * i + 1] = gr.y(); }
+  }
   return 0;
 }
 

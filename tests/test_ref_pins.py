@@ -2,7 +2,9 @@
 
 oracle/_ref/libref_pins.so is built by oracle/Makefile from fragments that oracle/extract_ref.py cuts, by line
 range, out of the reference where it lies: sdf_map.cpp:618-715 (updateESDF2d + fillESDF — rows E1/E2, including the
-window computation q4 and the aliasing quirks q1-q3), minco.hpp:43-198 (BandedSystem — M1), optimizer.cpp:573-591 and
+window computation q4 and the aliasing quirks q1-q3), sdf_map.cpp:453-472, :525-531, :739-871, :942-948 (the three
+getDistWithGradBilinear overloads, getDistanceReal, isOccWithSafeDis and their index helpers — E3/E4),
+minco.hpp:43-198 (BandedSystem — M1), optimizer.cpp:573-591 and
 :1069-1106 (tau <-> T maps, backwardGradT, positiveSmoothedL1 — M5/P4).  The fragments compile against the small Eigen
 stand-in in oracle/eigen_shim, which only supplies containers (no arithmetic of its own on these paths: element
 access, row views evaluated element by element, Vector2i as a tuple).  CPU only; the prebuilt library travels to
@@ -33,6 +35,7 @@ def ref():
     lib.ref_banded.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp]
     lib.ref_tmaps.argtypes = [C.c_int, dp, C.c_int, dp, dp]
     lib.ref_smoothed_l1.argtypes = [C.c_double, C.c_double, dp, dp]
+    lib.ref_dist_lookups.argtypes = [G, dp, C.c_int, dp, C.c_int, C.c_double, dp, dp]
     return lib
 
 
@@ -111,3 +114,62 @@ def test_time_maps_and_smoothed_l1_oracle_equals_reference_compiled(ref, orc):
             ref.ref_smoothed_l1(eps, float(x), C.byref(fa), C.byref(da))
             orc.orc_smoothed_l1(eps, float(x), C.byref(fb), C.byref(db))
             assert fa.value == fb.value and da.value == db.value
+
+
+def lookup_positions(geom, rng, n):
+    """Inside, on cell centres / edges, on and beyond the map bounds, in the last row / column (where the reference
+    refuses to interpolate)."""
+    gi = geom.grid_interval
+    p = np.empty((n, 2))
+    p[:, 0] = rng.uniform(geom.x_lower - 0.3, geom.x_upper + 0.3, n)
+    p[:, 1] = rng.uniform(geom.y_lower - 0.3, geom.y_upper + 0.3, n)
+    k = n // 4
+    p[:k, 0] = geom.x_lower + gi * rng.integers(0, geom.glx + 1, k)                   # cell edges
+    p[k:2 * k, 1] = geom.y_lower + gi * (rng.integers(0, geom.gly, k) + 0.5)          # cell centres
+    p[2 * k:2 * k + 8] = [(geom.x_lower, geom.y_lower), (geom.x_upper, geom.y_upper), (geom.x_lower, geom.y_upper),
+                          (geom.x_upper - 1e-12, geom.y_lower + 1e-12), (geom.x_upper - gi, geom.y_upper - gi),
+                          (geom.x_upper - 1.5 * gi, geom.y_upper - 0.5 * gi), (geom.x_lower + 0.5 * gi, geom.y_lower + 0.5 * gi),
+                          (geom.x_lower - 1e-9, geom.y_lower)]
+    return p
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_esdf_lookups_equal_reference_compiled(ref, seed):
+    """E3/E4: getDistWithGradBilinear (with mindis, with gradient, value only), getDistanceReal, isOccWithSafeDis —
+    oracle restatement and the host twins of SDFmap against the reference's own functions, bit for bit, including the
+    gradient the 3-argument overload leaves untouched when dist > mindis."""
+    rng = np.random.default_rng(40 + seed)
+    glx, gly = [(64, 48), (37, 91), (120, 120), (25, 25)][seed]
+    geom = workloads.make_geom(glx, gly, 0.0625)
+    grid = workloads.random_map(glx, gly, seed, p_occ=0.05, p_unknown=0.02)
+    dist = np.full(glx * gly, np.finfo(np.float64).max)
+    oracle_lib.esdf_update(geom, grid, (0, 0), (glx - 1, gly - 1), dist)
+    dist[dist > 1e300] = 7.25                      # cells the reference never writes: any finite stand-in, same for both
+    pos = lookup_positions(geom, rng, 4000)
+    n = len(pos)
+    olib = oracle_lib.load()
+    G = C.byref(geom)
+    for which, mindis in ((3, 0.4), (3, 1e9), (2, 0.0), (1, 0.0), (0, 0.0), (-1, 0.35)):
+        out = np.zeros(n)
+        sentinel = rng.normal(size=(n, 2))
+        gio = sentinel.copy()
+        ref.ref_dist_lookups(G, capi.dptr(dist), n, capi.dptr(np.ascontiguousarray(pos)), which, mindis, capi.dptr(out),
+                             capi.dptr(gio) if which >= 2 else None)
+        for i in range(n):
+            pi = np.ascontiguousarray(pos[i])
+            g = sentinel[i].copy()
+            if which == 3:
+                v = olib.orc_dist_grad3(G, capi.dptr(dist), capi.dptr(pi), capi.dptr(g), mindis)
+            elif which == 2:
+                v = olib.orc_dist_grad2(G, capi.dptr(dist), capi.dptr(pi), capi.dptr(g))
+            elif which == 1:
+                v = olib.orc_dist1(G, capi.dptr(dist), capi.dptr(pi))
+            elif which == 0:
+                v = olib.orc_dist_real(G, capi.dptr(dist), capi.dptr(pi))
+            else:
+                ix = min(max(int((pi[0] - geom.x_lower) * geom.inv_grid_interval), 0), glx - 1)
+                iy = min(max(int((pi[1] - geom.y_lower) * geom.inv_grid_interval), 0), gly - 1)
+                v = 1.0 if dist[ix * gly + iy] < mindis else 0.0
+            assert v == out[i], (which, i, pos[i], v, out[i])
+            if which >= 2:
+                assert g[0] == gio[i, 0] and g[1] == gio[i, 1], (which, i, pos[i], g, gio[i])
