@@ -15,7 +15,7 @@ echo "racecheck rc=$?" >> gpurun_out/racecheck_r02.pytest.txt
 ALORE_OPT_WAVE=1 compute-sanitizer --tool memcheck --error-exitcode 99 --log-file gpurun_out/memcheck_wave_r02.log \
   python -m pytest tests/test_optimizer_gpu.py -x -q -m gpu -k "config1 or batch_of_legs or collision_replans" > gpurun_out/memcheck_wave_r02.pytest.txt 2>&1
 echo "memcheck(wave) rc=$?" >> gpurun_out/memcheck_wave_r02.pytest.txt
-tail -3 gpurun_out/memcheck_r02.pytest.txt gpurun_out/racecheck_r02.pytest.txt gpurun_out/memcheck_wave_r02.pytest.txt
+tail -n 3 gpurun_out/memcheck_r02.pytest.txt gpurun_out/racecheck_r02.pytest.txt gpurun_out/memcheck_wave_r02.pytest.txt
 grep -h "ERROR SUMMARY" gpurun_out/memcheck_r02.log gpurun_out/racecheck_r02.log gpurun_out/memcheck_wave_r02.log
 # ESDF far-field path (K2 masks/flags, conditional K1b, K2e band envelope, warp-per-cell quirk column)
 compute-sanitizer --tool memcheck --error-exitcode 99 --log-file gpurun_out/memcheck_esdf_r02.log \
@@ -26,5 +26,5 @@ compute-sanitizer --tool racecheck --error-exitcode 99 --log-file gpurun_out/rac
   python -m pytest tests/test_alt_paths_gpu.py -x -q -m gpu -k "far_field and (knobs0 or knobs2)" \
   > gpurun_out/racecheck_esdf_r02.pytest.txt 2>&1
 echo "racecheck(esdf) rc=$?" >> gpurun_out/racecheck_esdf_r02.pytest.txt
-tail -3 gpurun_out/memcheck_esdf_r02.pytest.txt gpurun_out/racecheck_esdf_r02.pytest.txt
+tail -n 3 gpurun_out/memcheck_esdf_r02.pytest.txt gpurun_out/racecheck_esdf_r02.pytest.txt
 grep -h "ERROR SUMMARY" gpurun_out/memcheck_esdf_r02.log gpurun_out/racecheck_esdf_r02.log
