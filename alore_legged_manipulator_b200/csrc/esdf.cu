@@ -1231,16 +1231,17 @@ int alore_esdf_run(alore_ctx* ctx, const alore_map_geom_t* geom, const uint8_t* 
       esdf_row_pass<<<NX, ROW_THREADS, smem, st>>>(d_occ, (size_t)g.glx * g.gly, g.gly, min_x, min_y, NX, NY, ctx->d_row, pitch);
     if (ref_compat && NX >= 3 && NY >= 2) ALORE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // the aliased column forks here
     ctx->launches++;
-    if (!far_mask) {                                   // search path (ALORE_ESDF_NO_BAND / _DC): K2 itself prunes with the minima
-      launch_block_min(false);
-      ctx->launches++;
-      if (nblk > SB_MIN_BLOCKS) {
-        esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
-        ctx->launches++;
-      }
-    }
   } else if (ctx->row_pitch != pitch || !ctx->d_row) {
     return alore_fail(ctx, ALORE_EINVAL, "no retained row pass for this window");
+  }
+  if (!far_mask) {   // search path (ALORE_ESDF_NO_BAND / _DC): K2 itself prunes with the minima, ALL of them, also when the
+                     // retained row pass of a band-path update is re-used (that update filled only the tiles with far cells)
+    launch_block_min(false);
+    ctx->launches++;
+    if (nblk > SB_MIN_BLOCKS) {
+      esdf_superblock_min<<<dim3((pitch + 255) / 256, (nblk + SBLK - 1) / SBLK), 256, 0, st>>>(ctx->d_blk, pitch, nblk);
+      ctx->launches++;
+    }
   }
   const dim3 grid((NY + TY - 1) / TY, (NX + TX - 1) / TX);
   const bool quirk = ref_compat && NX >= 2 && NY >= 2;
